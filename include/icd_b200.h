@@ -1,0 +1,127 @@
+/*
+ * icd_b200.h — C ABI of the B200-native iCD hot path (libicd_b200.so).
+ *
+ * The reference (yandex-research/invertible-cd) has no native layer: every call below replaces a
+ * torch / diffusers-0.25.1 library call that the reference reaches from
+ *     utils/generation.py:241-244     model.unet(latents, t, timestep_cond=w_emb, encoder_hidden_states=ctx)
+ *     utils/generation_sdxl.py:288-295, 445-453   pipe.unet(..., added_cond_kwargs=...)
+ *     utils/p2p.py:321-342            explicit-probabilities attention (softmax(QK^T*scale) -> controller -> P.V)
+ *     utils/generation.py:136-155     predicted_origin (consistency update)
+ *     utils/generation.py:96-122      guidance_scale_embedding
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch); the library never allocates in a call
+ *     (CUDA-graph safe) except for a host-side cache of TMA descriptors;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - activations are fp16, channels-last: an image tensor is [B][H][W][C] == a token matrix [B*H*W][C];
+ *   - weights are fp16 [N][K] (K contiguous); 3x3 conv weights are [Cout][ky][kx][Cin];
+ *   - every function returns 0 on success, non-zero on error; icd_last_error() returns the message
+ *     (the Python host raises RuntimeError with it);
+ *   - one in-flight call per stream; not thread-safe by contract (mirrors the reference's single-threaded use).
+ */
+#ifndef ICD_B200_H_
+#define ICD_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* icd_last_error(void);
+/* library / device probe: returns 0 and fills sm_count, cc_major, cc_minor */
+int icd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+int icd_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores:  D = epilogue(alpha * A . B^T), fp32 accumulation.
+ * Replaces F.linear / F.conv2d(3x3, 1x1) / torch.baddbmm / torch.bmm of the U-Net forward
+ * (diffusers UNet2DConditionModel; call sites listed above).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct IcdGemm {
+  /* A operand (fp16). a_mode 0: A[z2][z1][m][k] with strides; a_mode 1: NHWC image(s), implicit 3x3 conv, pad 1 */
+  const void* a0;
+  const void* a1;          /* optional second source, concatenated after a0 along K (channel concat); may be NULL */
+  int a_mode;
+  int K0, K1;              /* K (or channel) extent of a0 / a1 */
+  long long a0_ld, a1_ld;  /* row (pixel) stride in elements */
+  long long a_z1_stride, a_z2_stride; /* batch strides in elements (a_mode 0) */
+  int ZA1;                 /* z = z2 * ZA1 + z1 */
+  int B, H, W;             /* a_mode 1: image batch and spatial size; M = B*H*W */
+  /* B operand (fp16): [N][K] K-contiguous (b_mn_major=0) or [K][N] N-contiguous (b_mn_major=1) */
+  const void* b;
+  long long b_ld;
+  long long b_z1_stride, b_z2_stride;
+  int ZB1;
+  int b_mn_major;
+  /* problem */
+  int M, N, K;             /* K = total reduction length per filter tap source (K0+K1), conv multiplies by 9 */
+  int Z;                   /* batch entries (1 for plain GEMM) */
+  /* epilogue */
+  float alpha;
+  const float* bias;       /* [N] fp32 or NULL */
+  const float* rowvec;     /* [M/rows_per_img][ldv] fp32 added per image, or NULL */
+  int rows_per_img;
+  int ldv;
+  const void* residual;    /* fp16 [M][ldr] or NULL */
+  long long ldr, res_zstride;
+  void* out;               /* fp16 or fp32 */
+  long long ldc, out_z1_stride, out_z2_stride, out_imgstride; /* batch offset = (z % ZA1)*z1 + (z / ZA1)*z2 */
+  int out_fp32;
+  int out_mode;            /* 0 row-major [M][ldc]; 1 transposed out[img][n][row_in_img] with column stride ldc */
+  int geglu;               /* B rows packed per BN tile as [h | gate]; out[:, j] = h_j * gelu(g_j); N counts packed rows */
+  int force_bn;            /* 0 = heuristic, else 64/128/160/256 */
+  /* fused consistency update on the (transposed, fp32) output — utils/generation.py:136-155 */
+  const float* upd_x;
+  float* upd_out;
+  float alpha_t, sigma_t, alpha_s, sigma_s;
+} IcdGemm;
+
+int icd_gemm(const IcdGemm* g, void* stream);
+/* N-tile width the heuristic (or force_bn) picks — the weight packer needs it for the GEGLU row interleave */
+int icd_gemm_pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention core (replaces F.scaled_dot_product_attention, and baddbmm+softmax+bmm of
+ * utils/p2p.py:335-338 when the controller does not edit the probabilities).
+ *   q: [B][Nq][H*D]  k,v: [B][Nk][H*D]  out: [B][Nq][H*D]   (row strides given in elements)
+ *   probs_out (optional): [B*H][Nq][probs_ld] fp16 normalised probabilities (AttentionStore capture)
+ * ------------------------------------------------------------------------------------------------ */
+int icd_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk, int D,
+                  long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale, void* probs_out,
+                  long long probs_ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Memory-bound kernels (HBM roofline): normalisations, activations, layout, embeddings, update.
+ * ------------------------------------------------------------------------------------------------ */
+/* GroupNorm(32 groups) [+ SiLU] over NHWC fp16; optional second source concatenated along C.
+ * stats_ws: fp32 workspace of 2*B*groups floats (zeroed by the call). Replaces F.group_norm + F.silu. */
+int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, void* y, int B, int HW, int groups, float eps,
+                  const float* gamma, const float* beta, int apply_silu, float* stats_ws, void* stream);
+/* LayerNorm over the last dim of [rows][C] fp16 -> fp16. Replaces F.layer_norm. */
+int icd_layernorm(const void* x, void* y, int rows, int C, float eps, const float* gamma, const float* beta,
+                  void* stream);
+/* In-place row softmax over [rows][ld] fp16 (first `cols` entries of each row); fp32 statistics. */
+int icd_softmax(void* x, long long rows, int cols, long long ld, void* stream);
+/* nearest-neighbour 2x upsample NHWC fp16 (Upsample2D interpolate). */
+int icd_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* gather for the stride-2 3x3 Downsample2D conv: y[B*Ho*Wo][9*C] from NHWC x (pad 1). */
+int icd_im2col_s2(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* NCHW fp32 latent -> NHWC fp16 with channels zero-padded to Cpad (conv_in operand). */
+int icd_latent_to_nhwc(const float* x, void* y, int B, int C, int HW, int Cpad, void* stream);
+/* sinusoidal embeddings: diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) -> [n][dim] fp16 = [cos | sin].
+ * freqs[dim/2] (fp32) is the frequency table; the host computes it once with the reference's fp32 op order so the
+ * sin/cos arguments are bit-identical to the reference's. */
+int icd_timestep_embedding(const float* t, const float* freqs, void* y, int n, int dim, void* stream);
+/* guidance_scale_embedding (utils/generation.py:96-122): [n] fp32 w -> [n][dim] fp16 = [sin | cos] of (1000 w) f_i */
+int icd_guidance_embedding(const float* w, const float* freqs, void* y, int n, int dim, void* stream);
+/* y = silu(x) elementwise fp16 (time-embedding MLP activations) */
+int icd_silu(const void* x, void* y, long long n, void* stream);
+/* fp16 -> fp16 elementwise add:  y = a + b */
+int icd_add(const void* a, const void* b, void* y, long long n, void* stream);
+/* consistency update (predicted_origin, utils/generation.py:136-155), fp32 NCHW, per-sample t/s scalars */
+int icd_consistency_update(const float* eps, const float* x, float* out, long long per_sample, int B,
+                           const float* alpha_t, const float* sigma_t, const float* alpha_s, const float* sigma_s,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICD_B200_H_ */

@@ -1,0 +1,371 @@
+// Fused attention core on tcgen05 tensor cores (flash-style online softmax), sm_100a.
+//
+//   O[b, q, h, :] = softmax_k( scale * Q[b, q, h, :] . K[b, k, h, :] ) . V[b, k, h, :]
+//
+// Replaces F.scaled_dot_product_attention (un-patched diffusers Attention: forward_cons_model and every SDXL
+// model) and the baddbmm -> softmax -> bmm sequence of the p2p-patched forward (utils/p2p.py:335-338) whenever the
+// controller only *reads* the probabilities; for cross-attention (N_kv <= 128) the normalised probabilities are
+// written out in the same pass (AttentionStore capture, utils/p2p.py:145-149) instead of being materialised by a
+// separate GEMM + softmax.
+//
+// One CTA = one (batch, head, 128-query tile); K/V stream through a 2-stage TMA ring in 128-key tiles.
+//   warp 0      TMA producer
+//   warp 1      MMA issuer:  S = Q.K^T  (M128 x N128 x D)  ->  TMEM[0,128)
+//                            O += P.V   (M128 x D x K128)   ->  TMEM[128,128+D)   (V consumed MN-major from smem)
+//   warps 2..5  softmax: one thread per query row; S read from TMEM twice (max pass, exp pass) to keep registers
+//               low enough for 2 CTAs/SM (the second CTA's MMAs fill the tensor pipe while this one does softmax);
+//               P written to 128B-swizzled smem as the A operand of the second MMA; O rescaled in TMEM only when
+//               a row maximum moved.
+#include <cuda_fp16.h>
+
+#include <string>
+
+#include "../../include/icd_b200.h"
+#include "host_util.h"
+#include "icd_ptx.cuh"
+
+namespace icd {
+
+int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_b[3],
+                 const uint32_t box[4]);
+
+struct AttnParams {
+  int B, H, Nq, Nk;
+  float scale_log2e;  // scale * log2(e)
+  __half* out;
+  long long out_ld;
+  __half* probs;      // optional [B*H][Nq][probs_ld]
+  long long probs_ld;
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int DP = (D + 15) / 16 * 16;      // MMA extent along the head dim
+  static constexpr int DATOMS = (D + 63) / 64;       // 64-wide (128 B) swizzle atoms along the head dim
+  static constexpr int KV_STAGES = DATOMS >= 3 ? 1 : 2;
+  static constexpr int TILE_BYTES = DATOMS * 16384;  // one Q / K / V tile of 128 rows
+  static constexpr int P_BYTES = 2 * 16384;          // 128 x 128 fp16 probabilities
+  static constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES + 256;
+  static constexpr int TMEM_COLS = (128 + DP) <= 256 ? 256 : 512;
+  static constexpr int MIN_CTAS = (DATOMS == 1) ? 2 : 1;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int DP = Cfg::DP, DATOMS = Cfg::DATOMS, ST = Cfg::KV_STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::TILE_BYTES;
+  uint8_t* sV = sK + ST * Cfg::TILE_BYTES;
+  uint8_t* sP = sV + ST * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // ST
+  uint64_t* v_full = bars + 1 + ST;   // ST
+  uint64_t* kv_empty = bars + 1 + 2 * ST;  // ST
+  uint64_t* s_full = bars + 1 + 3 * ST;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = s_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tiles = (p.Nq + 127) / 128;
+  const int qt = blockIdx.x % q_tiles;
+  const int bh = blockIdx.x / q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = qt * 128;
+  const int n_kv = (p.Nk + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  } else if (warp == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::TILE_BYTES);
+#pragma unroll
+      for (int a = 0; a < DATOMS; ++a) tma_load_4d(sQ + a * 16384, &tmQ, q_full, a * 64, h, q0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < DATOMS; ++a)
+          tma_load_4d(sK + stage * Cfg::TILE_BYTES + a * 16384, &tmK, &k_full[stage], a * 64, h, j * 128, b);
+        mbar_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < DATOMS; ++a)
+          tma_load_4d(sV + stage * Cfg::TILE_BYTES + a * 16384, &tmV, &v_full[stage], a * 64, h, j * 128, b);
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, DP, false, true);
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        // S = Q . K_j^T   (S is free: the softmax warps arrived on p_full(j-1) after reading it)
+        mbar_wait(&k_full[stage], phase);
+        tc_fence_after();
+        {
+          const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + stage * Cfg::TILE_BYTES);
+          int kstep = 0;
+#pragma unroll
+          for (int a = 0; a < DATOMS; ++a) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int kk_n = (DP - a * 64) >= 64 ? 4 : (DP - a * 64) / 16;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk < kk_n) {
+                umma_f16_ss(tmem_S, umma_smem_desc(qa + a * 16384 + kk * 32, 16, 1024),
+                            umma_smem_desc(ka + a * 16384 + kk * 32, 16, 1024), idesc_s, kstep != 0);
+                ++kstep;
+              }
+            }
+          }
+        }
+        umma_commit(s_full);
+        // O += P_j . V_j
+        mbar_wait(&v_full[stage], phase);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        {
+          const uint32_t pa = smem_u32(sP), va = smem_u32(sV + stage * Cfg::TILE_BYTES);
+          const int valid = min(128, p.Nk - j * 128);
+          const int ksteps = (valid + 15) / 16;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            umma_f16_ss(tmem_O, umma_smem_desc(pa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                        umma_smem_desc(va + ks * 2048, 16384, 1024), idesc_o, (j | ks) != 0);
+          }
+        }
+        umma_commit(&kv_empty[stage]);
+        umma_commit(o_full);
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;       // query row within the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int q = q0 + row;
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t p_row = smem_u32(sP) + row * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int valid = min(128, p.Nk - j * 128);
+      // pass 1: row maximum
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        if (c0 >= valid) break;
+        float s[32];
+        tmem_ld32(tmem_S + lane_off + c0, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < valid) m_tile = fmaxf(m_tile, s[i]);
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      const float m_scaled = m_new * p.scale_log2e;
+      const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // 0 on the first tile (m_run = -inf)
+      // pass 2: probabilities -> swizzled smem (fp16), row sum
+      float l_tile = 0.f;
+      if (j > 0) mbar_wait(o_full, (j - 1) & 1);  // previous P.V finished: P smem and O are ours again
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t packed[16];
+        if (c0 < valid) {
+          float s[32];
+          tmem_ld32(tmem_S + lane_off + c0, s);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e0 = (c0 + i < valid) ? exp2f(s[i] * p.scale_log2e - m_scaled) : 0.f;
+            float e1 = (c0 + i + 1 < valid) ? exp2f(s[i + 1] * p.scale_log2e - m_scaled) : 0.f;
+            const __half2 hh = __floats2half2_rn(e0, e1);
+            // accumulate what the tensor core will actually see (fp16-rounded), keeps P.V / l consistent
+            const float2 back = __half22float2(hh);
+            l_tile += back.x + back.y;
+            packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        }
+        // 32 columns = 4 x 16-byte chunks; chunk index within the 64-wide atom is XOR-swizzled with (row & 7)
+        const uint32_t atom_base = p_row + (c0 >> 6) * 16384;
+        const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint32_t addr = atom_base + (((chunk0 + cc) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * cc]),
+                       "r"(packed[4 * cc + 1]), "r"(packed[4 * cc + 2]), "r"(packed[4 * cc + 3])
+                       : "memory");
+        }
+      }
+      // rescale the running output if any row maximum of this warp moved
+      if (j > 0) {
+        const bool need = alpha != 1.0f;
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < DP; c0 += 16) {
+            float o[16];
+            tmem_ld16(tmem_O + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] *= alpha;
+            const uint32_t* r = reinterpret_cast<const uint32_t*>(o);
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                "%13, %14, %15, %16};" ::"r"(tmem_O + lane_off + c0),
+                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                : "memory");
+          }
+          tmem_st_wait();
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      // single-tile case: emit normalised probabilities (AttentionStore capture)
+      if (p.probs != nullptr && n_kv == 1 && q < p.Nq) {
+        const float inv = 1.f / l_run;
+        __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
+        for (int c = 0; c < valid; ++c) {
+          const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2;
+          unsigned short u;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
+          pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * inv);
+        }
+      }
+      fence_proxy_async_smem();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> fp16 -> global
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    __half* orow = p.out + (static_cast<long long>(b) * p.Nq + q) * p.out_ld + h * D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < DP; c0 += 16) {
+      float o[16];
+      tmem_ld16(tmem_O + lane_off + c0, o);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+        __half hv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hv[i] = __float2half_rn(o[i] * inv);
+        if (c0 + 16 <= D) {
+          reinterpret_cast<uint4*>(orow + c0)[0] = reinterpret_cast<const uint4*>(hv)[0];
+          reinterpret_cast<uint4*>(orow + c0)[1] = reinterpret_cast<const uint4*>(hv)[1];
+        } else if (c0 + 8 <= D) {
+          reinterpret_cast<uint4*>(orow + c0)[0] = reinterpret_cast<const uint4*>(hv)[0];
+          for (int i = 8; i < 16; ++i)
+            if (c0 + i < D) orow[c0 + i] = hv[i];
+        } else {
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < D) orow[c0 + i] = hv[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int D>
+static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                            cudaStream_t st) {
+  using Cfg = AttnCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(std::string("attention cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.B * p.H * ((p.Nq + 127) / 128);
+  attention_tc_kernel<D><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  return check_launch("attention_tc");
+}
+
+}  // namespace icd
+
+using namespace icd;
+
+extern "C" int icd_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
+                             int D, long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale,
+                             void* probs_out, long long probs_ld, void* stream) {
+  if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return set_error("icd_attention: null operand");
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return set_error("icd_attention: empty problem");
+  if (probs_out != nullptr && Nk > 128)
+    return set_error("icd_attention: probability capture is fused only for N_kv <= 128 (use the explicit path)");
+  if ((D % 8) != 0) return set_error("icd_attention: head dim must be a multiple of 8");
+  CUtensorMap tq, tk, tv;
+  // tensor maps over [B][N][H][D] as dims (d, head, token, batch): strides grow monotonically
+  const uint32_t box[4] = {64, 1, 128, 1};
+  {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nq, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)q_ld * 2, (uint64_t)q_ld * Nq * 2};
+    if (make_tmap_4d(&tq, q, dims, str, box)) return 1;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nk, (uint64_t)B};
+    const uint64_t strk[3] = {(uint64_t)D * 2, (uint64_t)k_ld * 2, (uint64_t)k_ld * Nk * 2};
+    if (make_tmap_4d(&tk, k, dims, strk, box)) return 1;
+    const uint64_t strv[3] = {(uint64_t)D * 2, (uint64_t)v_ld * 2, (uint64_t)v_ld * Nk * 2};
+    if (make_tmap_4d(&tv, v, dims, strv, box)) return 1;
+  }
+  AttnParams p;
+  p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__half*>(out);
+  p.out_ld = out_ld;
+  p.probs = reinterpret_cast<__half*>(probs_out);
+  p.probs_ld = probs_ld;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (D) {
+    case 40: return launch_attention<40>(tq, tk, tv, p, st);
+    case 64: return launch_attention<64>(tq, tk, tv, p, st);
+    case 80: return launch_attention<80>(tq, tk, tv, p, st);
+    case 160: return launch_attention<160>(tq, tk, tv, p, st);
+    default: return set_error("icd_attention: unsupported head dim (40, 64, 80, 160)");
+  }
+}

@@ -1,0 +1,280 @@
+// Host side of the tcgen05 GEMM: TMA descriptor construction (cached), tile-width heuristic, launch.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/icd_b200.h"
+#include "gemm_tc.cuh"
+#include "host_util.h"
+
+namespace icd {
+
+// ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || p == nullptr) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  uint64_t v[13];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) {
+      h ^= x;
+      h *= 1099511628211ull;
+    }
+    return static_cast<size_t>(h);
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mu;
+
+// fp16, rank-4, 128B swizzle. dims/box in elements, strides (dims 1..3) in bytes.
+int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_b[3],
+                 const uint32_t box[4]) {
+  TmapKey key;
+  key.v[0] = reinterpret_cast<uint64_t>(ptr);
+  for (int i = 0; i < 4; ++i) key.v[1 + i] = dims[i];
+  for (int i = 0; i < 3; ++i) key.v[5 + i] = strides_b[i];
+  for (int i = 0; i < 4; ++i) key.v[8 + i] = box[i];
+  key.v[12] = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uint64_t>(ptr) & 15) != 0) return set_error("TMA operand pointer must be 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    if ((strides_b[i] & 15) != 0) return set_error("TMA operand strides must be multiples of 16 bytes");
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_b[0], strides_b[1], strides_b[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  alignas(64) CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[512];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
+             "box=(%u,%u,%u,%u)",
+             static_cast<int>(r), (unsigned long long)dims[0], (unsigned long long)dims[1],
+             (unsigned long long)dims[2], (unsigned long long)dims[3], (unsigned long long)strides_b[0],
+             (unsigned long long)strides_b[1], (unsigned long long)strides_b[2], box[0], box[1], box[2], box[3]);
+    return set_error(buf);
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+static int pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn) {
+  if (force_bn != 0) return force_bn;
+  const int sms = sm_count();
+  const long long m_tiles = (M + 127) / 128;
+  const int cands_k[4] = {256, 160, 128, 64};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands_k[i];
+    if ((b_mn_major || geglu) && bn == 160) continue;
+    if (geglu && (N % bn) != 0) continue;
+    if (bn > 64 && N <= bn / 2) continue;  // mostly-empty tile
+    const long long tiles = m_tiles * ((N + bn - 1) / bn) * Z;
+    const long long waves = (tiles + sms - 1) / sms;
+    // per-tile time ~ MMA time (prop. to BN) + fixed epilogue/pipeline overhead
+    const double cost = static_cast<double>(waves) * (bn + 24);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
+                  cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long tiles = static_cast<long long>((p.M + 127) / 128) * ((p.N + BN - 1) / BN) * p.Z;
+  int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  if (grid < 1) grid = 1;
+  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("gemm_tc launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace icd
+
+using namespace icd;
+
+extern "C" int icd_gemm_pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn) {
+  return pick_bn(M, N, Z, geglu, b_mn_major, force_bn);
+}
+
+extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
+  if (g == nullptr || g->a0 == nullptr || g->b == nullptr || g->out == nullptr)
+    return set_error("icd_gemm: null operand");
+  if (g->M <= 0 || g->N <= 0 || g->Z <= 0) return set_error("icd_gemm: empty problem");
+  const int bn = pick_bn(g->M, g->N, g->Z, g->geglu, g->b_mn_major, g->force_bn);
+  if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error("icd_gemm: unsupported BN");
+  if (g->b_mn_major && (bn % 64) != 0) return set_error("icd_gemm: MN-major B needs BN multiple of 64");
+  if (g->geglu && (g->N % bn) != 0) return set_error("icd_gemm: GEGLU needs N % BN == 0");
+  if (g->a1 != nullptr && (g->K0 % 64) != 0) return set_error("icd_gemm: concat needs K0 % 64 == 0");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g->M;
+  p.N = g->N;
+  p.Z = g->Z;
+  p.ZA1 = g->ZA1 > 0 ? g->ZA1 : 1;
+  p.ZB1 = g->ZB1 > 0 ? g->ZB1 : 1;
+  p.a_mode = g->a_mode;
+  p.b_mn_major = g->b_mn_major;
+  const int kb0 = (g->K0 + 63) / 64;
+  const int kb1 = g->a1 != nullptr ? (g->K1 + 63) / 64 : 0;
+  p.kb_split = kb0;
+  p.kb_per_tap = kb0 + kb1;
+
+  CUtensorMap tmA0, tmA1, tmB;
+  if (g->a_mode == GEMM_A_CONV3X3) {
+    const int H = g->H, W = g->W, B = g->B;
+    if (W > 128 || (128 % W) != 0) return set_error("icd_gemm(conv): W must divide 128");
+    const int hw = H * W;
+    int tile_w = W, tile_h, tile_b;
+    if (hw >= 128) {
+      if ((hw % 128) != 0) return set_error("icd_gemm(conv): H*W must be a multiple of 128 (or divide it)");
+      tile_h = 128 / W;
+      tile_b = 1;
+    } else {
+      if ((128 % hw) != 0) return set_error("icd_gemm(conv): H*W must divide 128");
+      tile_h = H;
+      tile_b = 128 / hw;
+    }
+    if (g->M != B * hw) return set_error("icd_gemm(conv): M != B*H*W");
+    p.H = H; p.W = W; p.tile_w = tile_w; p.tile_h = tile_h; p.tile_b = tile_b;
+    p.num_kb = 9 * p.kb_per_tap;
+    const uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, (uint32_t)tile_b};
+    {
+      const uint64_t dims[4] = {(uint64_t)g->K0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      const uint64_t str[3] = {(uint64_t)g->a0_ld * 2, (uint64_t)g->a0_ld * W * 2, (uint64_t)g->a0_ld * hw * 2};
+      if (make_tmap_4d(&tmA0, g->a0, dims, str, box)) return 1;
+    }
+    if (g->a1 != nullptr) {
+      const uint64_t dims[4] = {(uint64_t)g->K1, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      const uint64_t str[3] = {(uint64_t)g->a1_ld * 2, (uint64_t)g->a1_ld * W * 2, (uint64_t)g->a1_ld * hw * 2};
+      if (make_tmap_4d(&tmA1, g->a1, dims, str, box)) return 1;
+    } else {
+      tmA1 = tmA0;
+    }
+  } else {
+    p.num_kb = p.kb_per_tap;
+    const uint64_t z2 = (uint64_t)((g->Z + p.ZA1 - 1) / p.ZA1);
+    const uint32_t box[4] = {64, 128, 1, 1};
+    {
+      const uint64_t dims[4] = {(uint64_t)g->K0, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
+      const uint64_t s1 = g->a_z1_stride > 0 ? (uint64_t)g->a_z1_stride * 2 : (uint64_t)g->a0_ld * 2;
+      const uint64_t s2 = g->a_z2_stride > 0 ? (uint64_t)g->a_z2_stride * 2 : s1;
+      const uint64_t str[3] = {(uint64_t)g->a0_ld * 2, s1, s2};
+      if (make_tmap_4d(&tmA0, g->a0, dims, str, box)) return 1;
+    }
+    if (g->a1 != nullptr) {
+      const uint64_t dims[4] = {(uint64_t)g->K1, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
+      const uint64_t s1 = g->a_z1_stride > 0 ? (uint64_t)g->a_z1_stride * 2 : (uint64_t)g->a1_ld * 2;
+      const uint64_t s2 = g->a_z2_stride > 0 ? (uint64_t)g->a_z2_stride * 2 : s1;
+      const uint64_t str[3] = {(uint64_t)g->a1_ld * 2, s1, s2};
+      if (make_tmap_4d(&tmA1, g->a1, dims, str, box)) return 1;
+    } else {
+      tmA1 = tmA0;
+    }
+  }
+  {
+    const uint64_t ktot = (uint64_t)p.num_kb * 64;  // weights are zero-padded to whole K blocks only when needed:
+    // the true extent is what the caller laid out; OOB columns are zero-filled by TMA.
+    const uint64_t kreal = g->a_mode == GEMM_A_CONV3X3 ? ktot : (uint64_t)(g->a1 != nullptr ? g->K0 + g->K1 : g->K0);
+    const uint64_t z2 = (uint64_t)((g->Z + p.ZB1 - 1) / p.ZB1);
+    const uint64_t s1 = g->b_z1_stride > 0 ? (uint64_t)g->b_z1_stride * 2 : (uint64_t)g->b_ld * 2;
+    const uint64_t s2 = g->b_z2_stride > 0 ? (uint64_t)g->b_z2_stride * 2 : s1;
+    const uint64_t str[3] = {(uint64_t)g->b_ld * 2, s1, s2};
+    const bool batched_b = g->b_z1_stride > 0 || g->b_z2_stride > 0;
+    if (g->b_mn_major) {
+      const uint64_t dims[4] = {(uint64_t)g->N, kreal, batched_b ? (uint64_t)p.ZB1 : 1, batched_b ? z2 : 1};
+      const uint32_t box[4] = {64, 64, 1, 1};
+      if (make_tmap_4d(&tmB, g->b, dims, str, box)) return 1;
+    } else {
+      const uint64_t dims[4] = {kreal, (uint64_t)g->N, batched_b ? (uint64_t)p.ZB1 : 1, batched_b ? z2 : 1};
+      const uint32_t box[4] = {64, (uint32_t)bn, 1, 1};
+      if (make_tmap_4d(&tmB, g->b, dims, str, box)) return 1;
+    }
+    p.b_batched = batched_b ? 1 : 0;
+  }
+
+  p.alpha = g->alpha;
+  p.bias = g->bias;
+  p.rowvec = g->rowvec;
+  p.rows_per_img = g->rows_per_img > 0 ? g->rows_per_img : g->M;
+  p.ldv = g->ldv;
+  p.residual = reinterpret_cast<const __half*>(g->residual);
+  p.ldr = g->ldr;
+  p.res_zstride = g->res_zstride;
+  p.out = g->out;
+  p.ldc = g->ldc;
+  p.out_z1_stride = g->out_z1_stride;
+  p.out_z2_stride = g->out_z2_stride;
+  p.out_imgstride = g->out_imgstride;
+  p.out_fp32 = g->out_fp32;
+  p.out_mode = g->out_mode;
+  p.geglu = g->geglu;
+  p.upd_x = g->upd_x;
+  p.upd_out = g->upd_out;
+  p.alpha_t = g->alpha_t; p.sigma_t = g->sigma_t; p.alpha_s = g->alpha_s; p.sigma_s = g->sigma_s;
+  if (p.upd_x != nullptr && !(p.out_fp32 && p.out_mode == GEMM_OUT_TRANSPOSED))
+    return set_error("icd_gemm: fused update needs fp32 transposed output");
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch<64>(tmA0, tmA1, tmB, p, st);
+    case 128: return launch<128>(tmA0, tmA1, tmB, p, st);
+    case 160: return launch<160>(tmA0, tmA1, tmB, p, st);
+    default: return launch<256>(tmA0, tmA1, tmB, p, st);
+  }
+}

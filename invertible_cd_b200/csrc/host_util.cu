@@ -1,0 +1,45 @@
+#include "host_util.h"
+
+#include "../../include/icd_b200.h"
+
+namespace icd {
+static thread_local std::string g_err;
+int set_error(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+      n = prop.multiProcessorCount;
+    else {
+      cudaGetLastError();
+      return 148;
+    }
+  }
+  return n;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+}  // namespace icd
+
+extern "C" const char* icd_last_error(void) { return icd::g_err.c_str(); }
+extern "C" int icd_abi_version(void) { return 1; }
+extern "C" int icd_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return icd::set_error("no CUDA device visible");
+  }
+  if (sms) *sms = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return 0;
+}

@@ -1,0 +1,267 @@
+// HBM-bound normalisation kernels: GroupNorm(+SiLU) over channels-last activations, LayerNorm, row softmax.
+// All loads/stores are 128-bit and coalesced along the channel axis; statistics are fp32 (GroupNorm partials
+// are combined in fp64) and the reductions are deterministic (no float atomics to global memory).
+#include <cuda_fp16.h>
+
+#include "../../include/icd_b200.h"
+#include "host_util.h"
+#include "icd_ptx.cuh"
+
+namespace icd {
+
+constexpr int GN_THREADS = 320;   // multiple of every (C/8) <= 320 that occurs: 40, 80, 160, 320 (120/240 leave idle lanes)
+constexpr int GN_MAX_CHUNKS = 64; // pixel chunks per image -> workspace = B * 64 * 2 * 32 floats
+
+struct GnSrc {
+  const __half* x0;
+  const __half* x1;
+  int C0, C1;
+};
+
+__device__ __forceinline__ const __half* gn_vec_ptr(const GnSrc& s, long long pix, int c) {
+  // channel c (multiple of 8) of pixel `pix` in the virtual concat [x0 | x1]
+  return c < s.C0 ? s.x0 + pix * s.C0 + c : s.x1 + pix * s.C1 + (c - s.C0);
+}
+
+// partial sums: ws[((b * chunks + chunk) * 2 + {0:sum,1:sumsq}) * 32 + g]
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW, int cpg, int chunks, float* ws) {
+  const int C = src.C0 + src.C1;
+  const int vpr = C >> 3;                      // 16-byte vectors per pixel
+  const int rows_per_iter = GN_THREADS / vpr;  // >= 1 (C <= 2560)
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int v = threadIdx.x % vpr, r = threadIdx.x / vpr;
+  const bool active = r < rows_per_iter;
+  const int c = v * 8;
+  const int g_lo = c / cpg;
+  __shared__ float s_sum[32], s_sq[32];
+  if (threadIdx.x < 32) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int rows_per_chunk = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * rows_per_chunk;
+  const int p1 = min(HW, p0 + rows_per_chunk);
+  float sl = 0.f, ql = 0.f, sh = 0.f, qh = 0.f;
+  const int split = (g_lo + 1) * cpg - c;  // elements j < split belong to g_lo, the rest to g_lo + 1
+  if (active) {
+    for (int pix = p0 + r; pix < p1; pix += rows_per_iter) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, static_cast<long long>(b) * HW + pix, c));
+      const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = __half2float(h[j]);
+        if (j < split) {
+          sl += x;
+          ql += x * x;
+        } else {
+          sh += x;
+          qh += x * x;
+        }
+      }
+    }
+    atomicAdd(&s_sum[g_lo], sl);
+    atomicAdd(&s_sq[g_lo], ql);
+    if (split < 8) {
+      atomicAdd(&s_sum[g_lo + 1], sh);
+      atomicAdd(&s_sq[g_lo + 1], qh);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float* o = ws + (static_cast<long long>(b) * chunks + chunk) * 64;
+    o[threadIdx.x] = s_sum[threadIdx.x];
+    o[32 + threadIdx.x] = s_sq[threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, int apply_chunks, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                const float* __restrict__ ws) {
+  const int C = src.C0 + src.C1;
+  const int vpr = C >> 3;
+  const int rows_per_iter = GN_THREADS / vpr;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  __shared__ float s_mean[32], s_rstd[32];
+  if (threadIdx.x < 32) {
+    double s = 0.0, q = 0.0;
+    const float* w = ws + static_cast<long long>(b) * chunks * 64;
+    for (int i = 0; i < chunks; ++i) {
+      s += static_cast<double>(w[i * 64 + threadIdx.x]);
+      q += static_cast<double>(w[i * 64 + 32 + threadIdx.x]);
+    }
+    const double n = static_cast<double>(HW) * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int v = threadIdx.x % vpr, r = threadIdx.x / vpr;
+  if (r >= rows_per_iter) return;
+  const int c = v * 8;
+  float a[8], sft[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    a[j] = s_rstd[g] * gamma[c + j];
+    sft[j] = beta[c + j] - s_mean[g] * a[j];
+  }
+  const int rows_per_chunk = (HW + apply_chunks - 1) / apply_chunks;
+  const int p0 = chunk * rows_per_chunk;
+  const int p1 = min(HW, p0 + rows_per_chunk);
+  for (int pix = p0 + r; pix < p1; pix += rows_per_iter) {
+    const long long gp = static_cast<long long>(b) * HW + pix;
+    const uint4 raw = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, gp, c));
+    const __half* h = reinterpret_cast<const __half*>(&raw);
+    uint4 outv;
+    __half* o = reinterpret_cast<__half*>(&outv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = __half2float(h[j]) * a[j] + sft[j];
+      if (do_silu) x = silu(x);
+      o[j] = __float2half_rn(x);
+    }
+    *reinterpret_cast<uint4*>(y + gp * C + c) = outv;
+  }
+}
+
+// one warp per row; values stay in registers between the mean and variance passes
+template <int MAXV>  // max 16-byte vectors per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows,
+                                                        int C, float eps, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const __half* xr = x + static_cast<long long>(warp) * C;
+  float vals[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xr + v * 8);
+      const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        vals[i][j] = __half2float(h[j]);
+        sum += vals[i][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = vals[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  __half* yr = y + static_cast<long long>(warp) * C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 outv;
+      __half* o = reinterpret_cast<__half*>(&outv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2half_rn((vals[i][j] - mean) * rstd * g[j] + bb[j]);
+      *reinterpret_cast<uint4*>(yr + v * 8) = outv;
+    }
+  }
+}
+
+// one warp per row, in place; three passes (row is L1/L2 resident)
+__global__ void __launch_bounds__(256) softmax_kernel(__half* __restrict__ x, long long rows, int cols, long long ld) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  __half* xr = x + warp * ld;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, __half2float(xr[c]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += __expf(__half2float(xr[c]) - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.f / s;
+  for (int c = lane; c < cols; c += 32) xr[c] = __float2half_rn(__expf(__half2float(xr[c]) - m) * inv);
+}
+
+}  // namespace icd
+
+using namespace icd;
+
+extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, void* y, int B, int HW, int groups,
+                             float eps, const float* gamma, const float* beta, int apply_silu, float* stats_ws,
+                             void* stream) {
+  const int C = C0 + (x1 != nullptr ? C1 : 0);
+  if (groups != 32) return set_error("icd_groupnorm: only 32 groups supported");
+  if (C % 32 != 0 || C0 % 8 != 0 || (x1 != nullptr && C1 % 8 != 0)) return set_error("icd_groupnorm: bad channels");
+  if (C / 8 > GN_THREADS) return set_error("icd_groupnorm: C > 2560 unsupported");
+  const int cpg = C / 32;
+  if (cpg < 8 && cpg != 0 && (8 % cpg) != 0) return set_error("icd_groupnorm: channels per group < 8 unsupported");
+  if (cpg < 8) return set_error("icd_groupnorm: channels per group < 8 unsupported");
+  GnSrc src{reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), C0, x1 != nullptr ? C1 : 0};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int chunks = (2 * sm_count() + B - 1) / B;
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+  if (chunks > HW) chunks = HW;
+  if (chunks < 1) chunks = 1;
+  gn_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, st>>>(src, HW, cpg, chunks, stats_ws);
+  if (check_launch("gn_stats")) return 1;
+  int apply_chunks = (4 * sm_count() + B - 1) / B;
+  if (apply_chunks > HW) apply_chunks = HW;
+  if (apply_chunks < 1) apply_chunks = 1;
+  gn_apply_kernel<<<dim3(apply_chunks, B), GN_THREADS, 0, st>>>(src, reinterpret_cast<__half*>(y), HW, cpg, chunks,
+                                                                apply_chunks, eps, gamma, beta, apply_silu, stats_ws);
+  return check_launch("gn_apply");
+}
+
+extern "C" int icd_layernorm(const void* x, void* y, int rows, int C, float eps, const float* gamma,
+                             const float* beta, void* stream) {
+  if (C % 8 != 0) return set_error("icd_layernorm: C must be a multiple of 8");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int warps_per_block = 8;
+  const int grid = (rows + warps_per_block - 1) / warps_per_block;
+  const int nvec = C / 8;
+  const __half* xp = reinterpret_cast<const __half*>(x);
+  __half* yp = reinterpret_cast<__half*>(y);
+  if (nvec <= 64)
+    layernorm_kernel<2><<<grid, 256, 0, st>>>(xp, yp, rows, C, eps, gamma, beta);
+  else if (nvec <= 160)
+    layernorm_kernel<5><<<grid, 256, 0, st>>>(xp, yp, rows, C, eps, gamma, beta);
+  else if (nvec <= 320)
+    layernorm_kernel<10><<<grid, 256, 0, st>>>(xp, yp, rows, C, eps, gamma, beta);
+  else
+    return set_error("icd_layernorm: C > 2560 unsupported");
+  return check_launch("layernorm");
+}
+
+extern "C" int icd_softmax(void* x, long long rows, int cols, long long ld, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long grid = (rows + 7) / 8;
+  softmax_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(reinterpret_cast<__half*>(x), rows, cols, ld);
+  return check_launch("softmax");
+}
