@@ -1,0 +1,271 @@
+"""iCD-XL sampler / inverter — the surface of utils/generation_sdxl.py (`sample_deterministic`,
+`inverse_sample_deterministic`, `DDIMSolver`, `compute_embeddings`, `guidance_scale_embedding`,
+`predicted_origin`, `linear_schedule_old`).
+
+Semantics kept: explicit `timesteps` lists are reversed / shifted into (t, s) pairs exactly as :262-266 and
+:397-402; no batch doubling and no p2p on this path; under dynamic guidance the *source* prompt embeddings are
+used while t > tau1*1000 and w follows `linear_schedule_old` (:431-442; the pooled `text_embeds` are not swapped);
+latents are cast back to the U-Net dtype (fp16) after every update (:297,463).
+Generalised: the reference's dynamic-guidance branch only works for batch 1 (`torch.tensor([tensor(B,)]*B)`
+raises, App. C-7); here `guidance_scale` may be a float or a per-sample vector.
+Not accelerated here: the two CLIP text encoders and the VAE. `compute_embeddings_fn` may return
+pre-computed embeddings; without a VAE on the pipe the functions return latents (image = None).
+"""
+import copy
+import random
+
+import numpy as np
+import torch
+
+from .generation import guidance_scale_embedding, predicted_origin, extract_into_tensor, linear_schedule_old  # noqa: F401
+
+
+def encode_prompt(prompt_batch, text_encoders, tokenizers, proportion_empty_prompts, is_train=True):
+    """Two-encoder SDXL prompt encoding (:9-46): hidden_states[-2] of both encoders concatenated, pooled output of
+    the last one."""
+    captions = []
+    for caption in prompt_batch:
+        if random.random() < proportion_empty_prompts:
+            captions.append("")
+        elif isinstance(caption, str):
+            captions.append(caption)
+        else:
+            captions.append(random.choice(caption) if is_train else caption[0])
+    embeds, pooled = [], None
+    with torch.no_grad():
+        for tokenizer, text_encoder in zip(tokenizers, text_encoders):
+            ids = tokenizer(captions, padding="max_length", max_length=tokenizer.model_max_length, truncation=True,
+                            return_tensors="pt").input_ids
+            out = text_encoder(ids.to(text_encoder.device), output_hidden_states=True)
+            pooled = out[0]
+            hs = out.hidden_states[-2]
+            embeds.append(hs.view(hs.shape[0], hs.shape[1], -1))
+    return torch.concat(embeds, dim=-1), pooled.view(len(captions), -1)
+
+
+def compute_embeddings(prompt_batch, original_sizes, crop_coords, proportion_empty_prompts, text_encoders,
+                       tokenizers, is_train=True, device='cuda'):
+    """-> {"prompt_embeds", "text_embeds", "time_ids"} with time_ids = [orig_h, orig_w, crop_t, crop_l, 1024, 1024]
+    (:49-76)."""
+    prompt_embeds, pooled = encode_prompt(prompt_batch, text_encoders, tokenizers, proportion_empty_prompts,
+                                          is_train)
+    return {"prompt_embeds": prompt_embeds.to(device), "text_embeds": pooled.to(device),
+            "time_ids": make_time_ids(original_sizes, crop_coords).to(device, dtype=prompt_embeds.dtype)}
+
+
+def make_time_ids(original_sizes, crop_coords, target_size=(1024, 1024)):
+    orig = torch.tensor(original_sizes, dtype=torch.long)
+    crop = torch.tensor(crop_coords, dtype=torch.long)
+    tgt = torch.tensor([list(target_size)]).repeat(orig.shape[0], 1)
+    return torch.cat([orig, crop, tgt], dim=-1)
+
+
+class DDIMSolver:
+    """Endpoint tables (:135-199); at inference only `.endpoints` / `.inverse_endpoints` are read, and only when no
+    explicit `timesteps` list is given."""
+
+    def __init__(self, alpha_cumprods, timesteps=1000, ddim_timesteps=50, num_endpoints=1, num_inverse_endpoints=1,
+                 max_inverse_timestep_index=49, endpoints=None, inverse_endpoints=None):
+        ratio = timesteps // ddim_timesteps
+        ts = (np.arange(1, ddim_timesteps + 1) * ratio).round().astype(np.int64) - 1
+        acp = np.asarray(alpha_cumprods)
+        self.ddim_timesteps = torch.from_numpy(ts).long()
+        self.ddim_alpha_cumprods = torch.from_numpy(acp[ts])
+        self.ddim_alpha_cumprods_prev = torch.from_numpy(np.asarray([acp[0]] + acp[ts[:-1]].tolist()))
+        self.ddim_alpha_cumprods_next = torch.from_numpy(np.asarray(acp[ts[1:]].tolist() + [0.0]))
+        if endpoints is None:
+            step = ddim_timesteps // num_endpoints + int(ddim_timesteps % num_endpoints > 0)
+            idx = torch.arange(step, ddim_timesteps, step) - 1
+            self.endpoints = torch.tensor([0] + self.ddim_timesteps[idx].tolist())
+        else:
+            self.endpoints = torch.tensor([int(e) for e in endpoints.split(',')])
+            assert len(self.endpoints) == num_endpoints
+        if inverse_endpoints is None:
+            step = ddim_timesteps // num_inverse_endpoints + int(ddim_timesteps % num_inverse_endpoints > 0)
+            idx = torch.arange(step, ddim_timesteps, step) - 1
+            idx = torch.tensor(idx.tolist() + [max_inverse_timestep_index])
+            self.inverse_endpoints = self.ddim_timesteps[idx]
+        else:
+            self.inverse_endpoints = torch.tensor([int(e) for e in inverse_endpoints.split(',')])
+            assert len(self.inverse_endpoints) == num_inverse_endpoints
+
+    def to(self, device):
+        for name in ("endpoints", "inverse_endpoints", "ddim_timesteps", "ddim_alpha_cumprods",
+                     "ddim_alpha_cumprods_prev", "ddim_alpha_cumprods_next"):
+            setattr(self, name, getattr(self, name).to(device))
+        return self
+
+    def ddim_step(self, pred_x0, pred_noise, timestep_index):
+        a = extract_into_tensor(self.ddim_alpha_cumprods_prev, timestep_index, pred_x0.shape)
+        return a.sqrt() * pred_x0 + (1.0 - a).sqrt() * pred_noise
+
+    def inverse_ddim_step(self, pred_x0, pred_noise, timestep_index):
+        a = extract_into_tensor(self.ddim_alpha_cumprods_next, timestep_index, pred_x0.shape)
+        return a.sqrt() * pred_x0 + (1.0 - a).sqrt() * pred_noise
+
+
+# ---------------------------------------------------------------------------------------------- internals
+def _batch_size(prompt):
+    if isinstance(prompt, str):
+        return 1
+    if isinstance(prompt, dict):
+        return prompt["prompt_embeds"].shape[0]
+    return len(prompt)
+
+
+def _embed(pipe, prompt, compute_embeddings_fn, is_sdxl):
+    """-> (prompt_embeds in unet dtype, added_cond_kwargs dict)."""
+    if isinstance(prompt, dict):                                 # pre-computed embeddings
+        enc = dict(prompt)
+    elif compute_embeddings_fn is not None:
+        if is_sdxl:
+            enc = dict(compute_embeddings_fn(prompt, [(1024, 1024)] * len(prompt), [(0, 0)] * len(prompt)))
+        else:
+            enc = {"prompt_embeds": compute_embeddings_fn(prompt)["prompt_embeds"]}
+    else:
+        raise RuntimeError("no compute_embeddings_fn and no pre-computed embeddings: text encoding is outside the "
+                           "accelerated path (SURVEY §8f)")
+    prompt_embeds = enc.pop("prompt_embeds").to(pipe.unet.dtype)
+    assert prompt_embeds.dtype == pipe.unet.dtype
+    return prompt_embeds, enc
+
+
+def _pairs_from_solver(pipe, num_scales, num_inference_steps, max_inverse_timestep_index, endpoints,
+                       inverse_endpoints, device):
+    solver = DDIMSolver(pipe.scheduler.alphas_cumprod.cpu().numpy(), timesteps=pipe.scheduler.num_train_timesteps,
+                        ddim_timesteps=num_scales, num_endpoints=num_inference_steps,
+                        num_inverse_endpoints=num_inference_steps,
+                        max_inverse_timestep_index=max_inverse_timestep_index, endpoints=endpoints,
+                        inverse_endpoints=inverse_endpoints).to(device)
+    return solver.inverse_endpoints.flip(0), solver.endpoints.flip(0)
+
+
+def _step(pipe, latents, t, s, prompt_embeds, w_embedding, added, alpha_schedule, sigma_schedule):
+    """One (t -> s) consistency step on B rows."""
+    unet = pipe.unet
+    ti, si = int(t), int(s)
+    if getattr(unet, "supports_cond_only", False) and pipe.scheduler.config.prediction_type == "epsilon":
+        a_s, s_s = (1.0, 0.0) if si == 0 else (alpha_schedule[si].item(), sigma_schedule[si].item())
+        upd = (latents.float().contiguous(), alpha_schedule[ti].item(), sigma_schedule[ti].item(), a_s, s_s)
+        out = unet(latents, t, encoder_hidden_states=prompt_embeds, timestep_cond=w_embedding,
+                   added_cond_kwargs=added, cross_attention_kwargs=None, return_dict=False, update=upd)
+        return out[1]
+    noise_pred = unet(latents, t, encoder_hidden_states=prompt_embeds, cross_attention_kwargs=None,
+                      return_dict=False, timestep_cond=w_embedding, added_cond_kwargs=added)[0]
+    n, dev = len(latents), latents.device
+    return predicted_origin(noise_pred, torch.tensor([ti] * n, device=dev), torch.tensor([si] * n, device=dev),
+                            latents, pipe.scheduler.config.prediction_type, alpha_schedule, sigma_schedule)
+
+
+def _w_embedding(pipe, w_rows, device, dtype):
+    w_rows = torch.as_tensor(w_rows, dtype=torch.float32).reshape(-1)
+    if hasattr(pipe.unet, "guidance_embedding"):
+        return pipe.unet.guidance_embedding(w_rows.to(device), 512)
+    return guidance_scale_embedding(w_rows, embedding_dim=512).to(device=device, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------------------------- public API
+@torch.no_grad()
+def inverse_sample_deterministic(pipe, images, prompt, generator=None, num_scales=50, num_inference_steps=1,
+                                 timesteps=None, start_timestep=19, max_inverse_timestep_index=49,
+                                 return_start_latent=False, guidance_scale=None, compute_embeddings_fn=None,
+                                 is_sdxl=False, inverse_endpoints=None, seed=0):
+    """Forward-consistency inversion image/latent -> noise latent (:204-310)."""
+    batch_size = _batch_size(prompt)
+    device = pipe._execution_device
+    prompt_embeds, added = _embed(pipe, prompt, compute_embeddings_fn, is_sdxl)
+    if timesteps is None:
+        ends = ','.join(['0'] + inverse_endpoints.split(',')[:-1]) if inverse_endpoints is not None else None
+        timesteps, boundary = _pairs_from_solver(pipe, num_scales, num_inference_steps, max_inverse_timestep_index,
+                                                 ends, inverse_endpoints, device)
+    else:
+        boundary = timesteps[1:] + [timesteps[0]]
+        boundary[-1] = 999
+        timesteps, boundary = torch.tensor(timesteps), torch.tensor(boundary)
+    alpha_schedule = torch.sqrt(pipe.scheduler.alphas_cumprod).to(device)
+    sigma_schedule = torch.sqrt(1 - pipe.scheduler.alphas_cumprod).to(device)
+
+    start_latents = _prepare_image_latents(pipe, images, timesteps[0], batch_size, prompt_embeds.dtype, device,
+                                           torch.Generator().manual_seed(seed))
+    latents = start_latents.clone()
+    w_embedding = None
+    if guidance_scale is not None:
+        w_embedding = _w_embedding(pipe, torch.ones(batch_size) * guidance_scale, device, latents.dtype)
+    for t, s in zip(timesteps, boundary):
+        latents = _step(pipe, latents.to(prompt_embeds.dtype), t, s, prompt_embeds, w_embedding, added,
+                        alpha_schedule, sigma_schedule).to(prompt_embeds.dtype)
+    return (latents, start_latents) if return_start_latent else latents
+
+
+@torch.no_grad()
+def sample_deterministic(pipe, prompt, latents=None, generator=None, num_scales=50, num_inference_steps=1,
+                         timesteps=None, start_timestep=19, max_inverse_timestep_index=49, return_latent=False,
+                         guidance_scale=None, compute_embeddings_fn=None, is_sdxl=False, endpoints=None,
+                         use_dynamic_guidance=False, tau1=0.7, tau2=0.7, amplify_prompt=None):
+    """Reverse-consistency generation / editing (:324-473)."""
+    size = pipe.unet.config.sample_size
+    batch_size = _batch_size(prompt)
+    device = pipe._execution_device
+    prompt_embeds, added = _embed(pipe, prompt, compute_embeddings_fn, is_sdxl)
+    amplify_embeds = None
+    if amplify_prompt is not None:
+        amplify_embeds, _ = _embed(pipe, amplify_prompt, compute_embeddings_fn, is_sdxl)   # pooled NOT swapped
+    prompt_embeds_init = copy.deepcopy(prompt_embeds)
+    if timesteps is None:
+        inv = ','.join(endpoints.split(',')[1:] + ['999']) if endpoints is not None else None
+        timesteps, boundary = _pairs_from_solver(pipe, num_scales, num_inference_steps, max_inverse_timestep_index,
+                                                 endpoints, inv, device)
+    else:
+        ts = list(reversed(copy.deepcopy(timesteps)))
+        boundary = ts[1:] + [ts[0]]
+        boundary[-1] = 0
+        timesteps, boundary = torch.tensor(ts), torch.tensor(boundary)
+    alpha_schedule = torch.sqrt(pipe.scheduler.alphas_cumprod).to(device)
+    sigma_schedule = torch.sqrt(1 - pipe.scheduler.alphas_cumprod).to(device)
+
+    if latents is None:
+        shape = (batch_size, pipe.unet.config.in_channels, size, size)
+        gen_dev = generator.device if generator is not None else "cpu"
+        latents = torch.randn(shape, generator=generator, device=gen_dev).to(device, dtype=prompt_embeds.dtype)
+        latents = latents * pipe.scheduler.init_noise_sigma
+    else:
+        latents = latents.to(device, dtype=prompt_embeds.dtype)
+
+    w_embedding = None
+    w = guidance_scale
+    if guidance_scale is not None:
+        w_embedding = _w_embedding(pipe, torch.ones(batch_size) * torch.as_tensor(guidance_scale, dtype=torch.float32),
+                                   device, latents.dtype)
+    for t, s in zip(timesteps, boundary):
+        if use_dynamic_guidance:
+            t_item = t if isinstance(t, int) else t.item()
+            use_src = t_item > tau1 * 1000 and amplify_embeds is not None
+            prompt_embeds = amplify_embeds if use_src else prompt_embeds_init
+            w_vec = torch.ones(batch_size) * torch.as_tensor(w, dtype=torch.float32)
+            w_vec = torch.tensor([linear_schedule_old(t_item, wi.item(), tau1=tau1, tau2=tau2) for wi in w_vec])
+            w_embedding = _w_embedding(pipe, w_vec, device, latents.dtype)
+        latents = _step(pipe, latents, t, s, prompt_embeds, w_embedding, added, alpha_schedule,
+                        sigma_schedule).to(pipe.unet.dtype)
+
+    image = None
+    if getattr(pipe, "vae", None) is not None:
+        pipe.vae.to(torch.float32)
+        image = pipe.vae.decode(latents.to(torch.float32) / pipe.vae.config.scaling_factor, return_dict=False)[0]
+        image = pipe.image_processor.postprocess(image, output_type="pil", do_denormalize=[True] * image.shape[0])
+    return (image, latents) if return_latent else image
+
+
+def _prepare_image_latents(pipe, images, timestep, batch_size, dtype, device, generator):
+    """Img2Img `prepare_latents` (:273): encode (or accept 4-channel latents as-is), then add noise at `timestep`
+    with a CPU generator."""
+    images = images.to(device=device, dtype=dtype)
+    if images.shape[1] == 4:
+        init = images
+    else:
+        if getattr(pipe, "vae", None) is None:
+            raise RuntimeError("image inputs need a VAE; pass (B,4,128,128) latents (SURVEY §8f)")
+        init = pipe.vae.encode(images).latent_dist.sample(generator) * pipe.vae.config.scaling_factor
+    if init.shape[0] != batch_size:
+        init = init.repeat(batch_size // init.shape[0], 1, 1, 1)
+    noise = torch.randn(init.shape, generator=generator).to(device=device, dtype=dtype)
+    return pipe.scheduler.add_noise(init, noise, torch.as_tensor(timestep).reshape(1))

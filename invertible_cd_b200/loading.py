@@ -1,0 +1,228 @@
+"""Model loading for the iCD path: teacher + reverse/forward consistency students with LoRA fused at load.
+
+Public surface of utils/loading.py (`load_models`, `load_models_xl`, `get_module_kohya_state_dict`) with the same
+signatures and return order.  Differences forced by this build: there is no diffusers here, so a "pipeline" is a
+light `ICDPipeline` container exposing exactly the attributes the loop touches (`.unet .vae
+.tokenizer .text_encoder .scheduler .device .dtype`), `.unet` is a `B200UNet`, and the LoRA adapters are fused
+into the packed fp16 weights by `fuse_lora` below (W += alpha/r * B.A, alpha = 8) instead of going
+through `load_lora_weights` + `fuse_lora` of diffusers (utils/loading.py:66-71).
+`model_id` may be
+  * a local directory in diffusers layout (`unet/config.json` + `unet/diffusion_pytorch_model.safetensors`;
+    optional `text_encoder/`, `tokenizer/` loaded with transformers when present), or
+  * "synthetic:<sd15|sdxl|small_sd15|small_sdxl>[:seed]" — random-init weights of the exact architecture (there
+    is no network access for real checkpoints on the benchmark boxes).
+"""
+import json
+import os
+from collections import OrderedDict
+
+import torch
+
+from . import arch
+from .schedulers import DDIMScheduler, DDPMScheduler
+from .unet import B200UNet
+
+LORA_ALPHA = 8  # utils/loading.py:19-21 (peft default lora_alpha with LoraConfig(r=...))
+
+
+class ICDPipeline:
+    """Attribute bag standing in for StableDiffusion(XL)(Img2Img)Pipeline on the iCD path."""
+
+    def __init__(self, unet, scheduler, vae=None, tokenizer=None, text_encoder=None, device="cuda",
+                 dtype=torch.float32, tokenizer_2=None, text_encoder_2=None):
+        self.unet, self.scheduler, self.vae = unet, scheduler, vae
+        self.tokenizer, self.text_encoder = tokenizer, text_encoder
+        self.tokenizer_2, self.text_encoder_2 = tokenizer_2, text_encoder_2
+        self.device, self.dtype = torch.device(device), dtype
+        self.vae_scale_factor = 8
+
+    @property
+    def _execution_device(self):
+        return self.device
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def clone_with_unet(self, unet):
+        return ICDPipeline(unet, self.scheduler, self.vae, self.tokenizer, self.text_encoder, self.device, self.dtype,
+                           self.tokenizer_2, self.text_encoder_2)
+
+
+def get_module_kohya_state_dict(module, prefix: str, dtype: torch.dtype, adapter_name: str = "default"):
+    """peft LoRA keys -> kohya keys with alpha = 8 for every adapted module (utils/loading.py:10-23)."""
+    out = {}
+    for peft_key, weight in module.items():
+        key = peft_key.replace("unet.base_model.model", prefix)
+        key = key.replace("lora_A", "lora_down").replace("lora_B", "lora_up")
+        key = key.replace(".", "_", key.count(".") - 2)
+        out[key] = weight.to(dtype)
+        if "lora_down" in key:
+            out[f'{key.split(".")[0]}.alpha'] = torch.tensor(LORA_ALPHA).to(dtype)
+    return out
+
+
+def fuse_lora(state_dict, lora_weights, r=64, lora_dtype=torch.float16, alpha=LORA_ALPHA):
+    """Return a copy of `state_dict` with W <- W + (alpha/r) * B.A for every adapted module.
+    `lora_weights`: peft-format dict (`unet.base_model.model.<module>.lora_{A,B}.weight`). A and B are first cast to
+    `lora_dtype` (fp16 for SD1.5, utils/loading.py:68,82; fp32 for SDXL, :122,141), the product is formed in fp32
+    and the sum is cast back to the weight dtype. Conv adapters: mm(B.flatten(1), A.flatten(1)).reshape(W.shape)."""
+    fused = OrderedDict(state_dict)
+    prefix = "unet.base_model.model."
+    mods = sorted({k[len(prefix):].rsplit(".lora_", 1)[0] for k in lora_weights if k.startswith(prefix)})
+    if not mods and lora_weights:
+        raise ValueError("fuse_lora: no peft-format keys ('unet.base_model.model.*.lora_A.weight') found")
+    for mod in mods:
+        wkey = mod + ".weight"
+        if wkey not in fused:
+            raise KeyError(f"LoRA adapter for unknown module {mod}")
+        A = lora_weights[f"{prefix}{mod}.lora_A.weight"].to(lora_dtype).float()
+        Bm = lora_weights[f"{prefix}{mod}.lora_B.weight"].to(lora_dtype).float()
+        rank = A.shape[0]
+        W = fused[wkey]
+        delta = torch.mm(Bm.flatten(1).to(W.device), A.flatten(1).to(W.device)).reshape(W.shape)
+        fused[wkey] = (W.float() + (alpha / rank) * delta).to(W.dtype)
+    return fused
+
+
+# ---------------------------------------------------------------------------------------------- sources
+def _parse_synthetic(model_id):
+    parts = model_id.split(":")
+    name = parts[1] if len(parts) > 1 else "sd15"
+    seed = int(parts[2]) if len(parts) > 2 else 0
+    if name not in arch.NAMED_CONFIGS:
+        raise ValueError(f"unknown synthetic model '{name}' (have {sorted(arch.NAMED_CONFIGS)})")
+    return name, seed
+
+
+def _load_tensor_file(path):
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu")
+
+
+def _unet_source(model_id, w_embed_dim, is_xl):
+    """-> (config, state_dict on CPU, text parts dict)."""
+    if isinstance(model_id, str) and model_id.startswith("synthetic"):
+        name, seed = _parse_synthetic(model_id)
+        cfg = arch.NAMED_CONFIGS[name](time_cond_proj_dim=w_embed_dim if w_embed_dim > 0 else None)
+        return cfg, arch.synthetic_state_dict(cfg, seed=seed), {}
+    if not os.path.isdir(model_id):
+        raise FileNotFoundError(f"model_id '{model_id}' is neither a local diffusers directory nor 'synthetic:*' "
+                                "(no network access: hub ids cannot be resolved)")
+    with open(os.path.join(model_id, "unet", "config.json")) as f:
+        raw = json.load(f)
+    fields = {k: raw[k] for k in arch.UNetConfig.__dataclass_fields__ if k in raw}
+    n_levels = len(raw["block_out_channels"])
+    for k in ("attention_head_dim", "transformer_layers_per_block"):
+        v = fields.get(k, 1)
+        fields[k] = tuple(v) if isinstance(v, (list, tuple)) else (v,) * n_levels
+    for k in ("block_out_channels", "down_block_types", "up_block_types"):
+        fields[k] = tuple(fields[k])
+    fields["time_cond_proj_dim"] = w_embed_dim if w_embed_dim > 0 else None
+    cfg = arch.UNetConfig(**fields)
+    sd = None
+    for fname in ("diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.safetensors",
+                  "diffusion_pytorch_model.bin"):
+        p = os.path.join(model_id, "unet", fname)
+        if os.path.exists(p):
+            sd = _load_tensor_file(p)
+            break
+    if sd is None:
+        raise FileNotFoundError(f"no U-Net weights under {model_id}/unet")
+    if cfg.time_cond_proj_dim and "time_embedding.cond_proj.weight" not in sd:
+        # from_pretrained(time_cond_proj_dim=...) creates the layer with default init; the teacher .pt overwrites it
+        sd["time_embedding.cond_proj.weight"] = torch.zeros(cfg.block_out_channels[0], cfg.time_cond_proj_dim)
+    text = {}
+    try:
+        from transformers import CLIPTextModel, CLIPTokenizer
+        if os.path.isdir(os.path.join(model_id, "tokenizer")):
+            text["tokenizer"] = CLIPTokenizer.from_pretrained(os.path.join(model_id, "tokenizer"))
+        if os.path.isdir(os.path.join(model_id, "text_encoder")):
+            text["text_encoder"] = CLIPTextModel.from_pretrained(os.path.join(model_id, "text_encoder"))
+    except Exception as e:  # text encoding is an input producer, not part of the accelerated path
+        print(f"[loading] text encoder/tokenizer not loaded: {e}")
+    return cfg, sd, text
+
+
+def _validate(cfg, sd):
+    shapes = arch.unet_param_shapes(cfg)
+    missing = [k for k in shapes if k not in sd]
+    bad = [k for k in shapes if k in sd and tuple(sd[k].shape) != tuple(shapes[k])]
+    if missing or bad:
+        raise RuntimeError(f"U-Net state dict mismatch: {len(missing)} missing (e.g. {missing[:3]}), "
+                           f"{len(bad)} wrong shape (e.g. {bad[:3]})")
+
+
+def _lora_source(spec, cfg, r):
+    if spec is None:
+        return None
+    if isinstance(spec, dict):
+        return spec
+    if isinstance(spec, str) and spec.startswith("synthetic"):
+        parts = spec.split(":")
+        return arch.synthetic_lora(cfg, r=r, seed=int(parts[1]) if len(parts) > 1 else 1)
+    return _load_tensor_file(spec)
+
+
+# ---------------------------------------------------------------------------------------------- public API
+def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, w_embed_dim=0,
+                teacher_checkpoint=None, dtype='fp32'):
+    """-> (ldm_stable, reverse_cons_model, forward_cons_model), as utils/loading.py:27-90.
+    `dtype` selects the dtype of the latents the loop carries ('fp32'/'fp16'); the U-Net kernels always compute in
+    fp16 with fp32 accumulation (documented deviation: the reference's fp32 editing mode runs fp32 cuBLAS/cuDNN)."""
+    tdtype = torch.float32 if dtype == 'fp32' else torch.float16
+    scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                              set_alpha_to_one=False)
+    cfg, sd, text = _unet_source(model_id, w_embed_dim, is_xl=False)
+    if w_embed_dim > 0:
+        print(f'Forward CD is initialized with guidance embedding, dim {w_embed_dim}')
+        if teacher_checkpoint is not None:
+            print(f'Embedded model is loading from {teacher_checkpoint}')
+            sd = teacher_checkpoint if isinstance(teacher_checkpoint, dict) else _load_tensor_file(teacher_checkpoint)
+        elif not str(model_id).startswith("synthetic"):
+            print('PROVIDE TEACHER')
+    _validate(cfg, sd)
+    text_encoder = text.get("text_encoder")
+    if text_encoder is not None:
+        text_encoder = text_encoder.to(device)
+    ldm_stable = ICDPipeline(B200UNet(cfg, sd, device), scheduler, None, text.get("tokenizer"), text_encoder,
+                             device, tdtype)
+    students = []
+    for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
+        if ckpt is None:
+            students.append(None)
+            continue
+        print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')
+        fused = fuse_lora(sd, _lora_source(ckpt, cfg, r), r=r, lora_dtype=torch.float16)
+        students.append(ldm_stable.clone_with_unet(B200UNet(cfg, fused, device)))
+    return ldm_stable, students[0], students[1]
+
+
+def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_checkpoint, device="cuda", r=64):
+    """-> (stable_pipe, pipe, forw_pipe), as utils/loading.py:93-147 (fp16 base, LoRA kept fp32 for the fuse)."""
+    cfg, sd, text = _unet_source(model_id, 512, is_xl=True)
+    if teacher_checkpoint is not None:
+        sd = teacher_checkpoint if isinstance(teacher_checkpoint, dict) else _load_tensor_file(teacher_checkpoint)
+    sd = OrderedDict((k, v.to(torch.float16)) for k, v in sd.items())
+    _validate(cfg, sd)
+    scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    scheduler.num_train_timesteps = 1000
+    stable_pipe = ICDPipeline(B200UNet(cfg, sd, device), scheduler, None, text.get("tokenizer"),
+                              text.get("text_encoder"), device, torch.float16)
+    pipes = []
+    for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
+        print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')
+        fused = fuse_lora(sd, _lora_source(ckpt, cfg, r), r=r, lora_dtype=torch.float32)
+        pipes.append(stable_pipe.clone_with_unet(B200UNet(cfg, fused, device)))
+    return stable_pipe, pipes[0], pipes[1]
+
+
+def load_benchmark(path_to_prompts, path_to_images=None):
+    """CSV reader of utils/loading.py:151-175 (kept for interface completeness; not on the accelerated path)."""
+    import pandas as pd
+    files = pd.read_csv(path_to_prompts)
+    if path_to_images is None:
+        return list(files['caption']), list(files['file_name'])
+    return [(f"{path_to_images}/{row['file_name']}", {'before': row['old_caption'], 'after': row['edited_caption']},
+             row['blended_words']) for _, row in files.reset_index().iterrows()]

@@ -1,0 +1,347 @@
+"""B200 U-Net executor: the drop-in for `diffusers.UNet2DConditionModel.forward` on the iCD path.
+
+Replaces the call the reference makes at utils/generation.py:208,241-244 and utils/generation_sdxl.py:288-295,
+445-453:   unet(sample, t, encoder_hidden_states=ctx, timestep_cond=w_emb, added_cond_kwargs=...)["sample"] / [0].
+
+Host code is Python (as the reference's is); all arithmetic runs in hand-written sm_100a kernels reached through
+the C ABI (invertible_cd_b200/ops.py -> libicd_b200.so).  There is no PyTorch-eager or CPU fallback.
+
+Data layout in HBM
+  activations  fp16 channels-last token matrices [rows*H*W, C]  (an NHWC image IS the transformer token matrix,
+               so ResNet blocks and transformer blocks hand tensors to each other without a transpose)
+  weights      fp16 [N, K] K-contiguous; 3x3 convs [Cout, (ky,kx,cin)]; q|k|v and k|v projections concatenated;
+               GEGLU rows interleaved per 256-wide N tile; all 22/17 time_emb_proj matrices concatenated into one
+  latents      fp32 NCHW at the boundary (what the reference's loop carries)
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .packing import pack_conv3x3, pack_geglu, pack_linear
+
+GEGLU_BN = 256
+
+
+class UNetOutput(dict):
+    """`["sample"]`, `.sample` and `[0]` access like diffusers' UNet2DConditionOutput."""
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self, "sample" if k == 0 else k)
+
+    @property
+    def sample(self):
+        return dict.__getitem__(self, "sample")
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class B200UNet:
+    """Packed weights + forward of one U-Net (teacher, forward-consistency or reverse-consistency model)."""
+
+    def __init__(self, config, state_dict, device="cuda"):
+        self.config = config if not isinstance(config, dict) else SimpleNamespace(**config)
+        self.device = torch.device(device)
+        self.controller = None          # set by p2p.register_attention_control
+        self.attn_places = []           # execution-ordered ('down'|'mid'|'up') per Attention module
+        self._pack(state_dict)
+        self._freq_cache = {}
+
+    supports_cond_only = True       # rows may be the conditional half only (host logic in generation.py)
+
+    # ------------------------------------------------------------------ reference-visible attributes
+    @property
+    def dtype(self):
+        return torch.float16            # compute dtype of the kernels (utils/generation.py:241 casts inputs to it)
+
+    @property
+    def in_channels(self):
+        return self.config.in_channels
+
+    @property
+    def num_attention_layers(self):
+        return len(self.attn_places)
+
+    def named_children(self):
+        return iter(())
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------ packing
+    def _pack(self, sd):
+        cfg, dev = self.config, self.device
+        g = lambda k: sd[k]
+        boc = list(cfg.block_out_channels)
+        self.temb_ch = boc[0] * 4
+        temb_w, temb_b = [], []
+        self._temb_off = 0
+
+        def conv(prefix):
+            return SimpleNamespace(w=pack_conv3x3(g(prefix + ".weight")).to(dev), b=_f32(g(prefix + ".bias"), dev))
+
+        def lin(prefix, bias=True):
+            return SimpleNamespace(w=pack_linear(g(prefix + ".weight")).to(dev),
+                                   b=_f32(g(prefix + ".bias"), dev) if bias else None)
+
+        def norm(prefix):
+            return SimpleNamespace(g=_f32(g(prefix + ".weight"), dev), b=_f32(g(prefix + ".bias"), dev))
+
+        def res(prefix, cin, cout):
+            r = SimpleNamespace(cin=cin, cout=cout, norm1=norm(prefix + ".norm1"), conv1=conv(prefix + ".conv1"),
+                                norm2=norm(prefix + ".norm2"), conv2=conv(prefix + ".conv2"), temb_off=self._temb_off,
+                                shortcut=lin(prefix + ".conv_shortcut") if cin != cout else None)
+            temb_w.append(g(prefix + ".time_emb_proj.weight"))
+            temb_b.append(g(prefix + ".time_emb_proj.bias"))
+            self._temb_off += cout
+            return r
+
+        def attn_block(prefix, C, heads, place):
+            a1, a2 = prefix + ".attn1", prefix + ".attn2"
+            w1, b1 = pack_geglu(g(prefix + ".ff.net.0.proj.weight").to(dev), g(prefix + ".ff.net.0.proj.bias").to(dev),
+                                GEGLU_BN)
+            blk = SimpleNamespace(
+                ln1=norm(prefix + ".norm1"), ln2=norm(prefix + ".norm2"), ln3=norm(prefix + ".norm3"),
+                qkv=torch.cat([pack_linear(g(a1 + f".to_{n}.weight")) for n in "qkv"], 0).to(dev),
+                out1=lin(a1 + ".to_out.0"),
+                q2=pack_linear(g(a2 + ".to_q.weight")).to(dev),
+                kv2=torch.cat([pack_linear(g(a2 + f".to_{n}.weight")) for n in "kv"], 0).to(dev),
+                out2=lin(a2 + ".to_out.0"),
+                ff1=SimpleNamespace(w=w1, b=b1), ff2=lin(prefix + ".ff.net.2"))
+            self.attn_places += [place, place]
+            return blk
+
+        def tfm(prefix, C, heads, depth, place):
+            return SimpleNamespace(C=C, heads=heads, d=C // heads, norm=norm(prefix + ".norm"),
+                                   proj_in=lin(prefix + ".proj_in"), proj_out=lin(prefix + ".proj_out"),
+                                   blocks=[attn_block(f"{prefix}.transformer_blocks.{k}", C, heads, place)
+                                           for k in range(depth)])
+
+        heads, depth = list(cfg.attention_head_dim), list(cfg.transformer_layers_per_block)
+        lpb = cfg.layers_per_block
+        self.conv_in = conv("conv_in")
+        te = "time_embedding"
+        self.time_lin1, self.time_lin2 = lin(te + ".linear_1"), lin(te + ".linear_2")
+        self.cond_proj = (pack_linear(g(te + ".cond_proj.weight")).to(dev)
+                          if getattr(cfg, "time_cond_proj_dim", None) else None)
+        self.is_xl = getattr(cfg, "addition_embed_type", None) == "text_time"
+        if self.is_xl:
+            self.add_lin1, self.add_lin2 = lin("add_embedding.linear_1"), lin("add_embedding.linear_2")
+
+        self.down = []
+        out_ch = boc[0]
+        for i, t in enumerate(cfg.down_block_types):
+            in_ch, out_ch = out_ch, boc[i]
+            has_attn = t == "CrossAttnDownBlock2D"
+            blk = SimpleNamespace(resnets=[], attns=[] if has_attn else None, down=None)
+            for j in range(lpb):
+                blk.resnets.append(res(f"down_blocks.{i}.resnets.{j}", in_ch if j == 0 else out_ch, out_ch))
+                if has_attn:
+                    blk.attns.append(tfm(f"down_blocks.{i}.attentions.{j}", out_ch, heads[i], depth[i], "down"))
+            if i != len(boc) - 1:
+                blk.down = conv(f"down_blocks.{i}.downsamplers.0.conv")
+            self.down.append(blk)
+        self.mid = SimpleNamespace(
+            res0=res("mid_block.resnets.0", boc[-1], boc[-1]),
+            attn=tfm("mid_block.attentions.0", boc[-1], heads[-1], depth[-1], "mid"),
+            res1=res("mid_block.resnets.1", boc[-1], boc[-1]))
+        self.up = []
+        rboc, rheads, rdepth = boc[::-1], heads[::-1], depth[::-1]
+        out_ch = rboc[0]
+        for i, t in enumerate(cfg.up_block_types):
+            prev, out_ch = out_ch, rboc[i]
+            in_ch = rboc[min(i + 1, len(boc) - 1)]
+            has_attn = t == "CrossAttnUpBlock2D"
+            blk = SimpleNamespace(resnets=[], attns=[] if has_attn else None, up=None)
+            for j in range(lpb + 1):
+                skip = in_ch if j == lpb else out_ch
+                rin = prev if j == 0 else out_ch
+                blk.resnets.append(res(f"up_blocks.{i}.resnets.{j}", rin + skip, out_ch))
+                if has_attn:
+                    blk.attns.append(tfm(f"up_blocks.{i}.attentions.{j}", out_ch, rheads[i], rdepth[i], "up"))
+            if i != len(boc) - 1:
+                blk.up = conv(f"up_blocks.{i}.upsamplers.0.conv")
+            self.up.append(blk)
+        self.norm_out = norm("conv_norm_out")
+        self.conv_out = conv("conv_out")
+        # one GEMM for every ResnetBlock2D.time_emb_proj of the network
+        self.temb_all = SimpleNamespace(w=torch.cat([pack_linear(w) for w in temb_w], 0).to(dev),
+                                        b=torch.cat([_f32(b, dev) for b in temb_b], 0))
+
+    # ------------------------------------------------------------------ embeddings
+    def _freqs(self, kind, dim):
+        key = (kind, dim)
+        if key not in self._freq_cache:
+            half = dim // 2
+            if kind == "t":     # diffusers get_timestep_embedding(freq_shift=0), fp32 op order
+                f = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+            else:               # guidance_scale_embedding, utils/generation.py:114-116 (fp32 op order)
+                e = torch.log(torch.tensor(10000.0)) / (half - 1)
+                f = torch.exp(torch.arange(half, dtype=torch.float32) * -e)
+            self._freq_cache[key] = f.to(self.device)
+        return self._freq_cache[key]
+
+    def guidance_embedding(self, w, dim=512):
+        """w: fp32 [rows] device tensor -> fp16 [rows, dim] (utils/generation.py:96-122)."""
+        return ops.guidance_embedding(w, self._freqs("w", dim), dim)
+
+    def _time_embed(self, rows, timestep, timestep_cond, added):
+        dev = self.device
+        if torch.is_tensor(timestep):
+            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+            if t.numel() == 1:
+                t = t.expand(rows)
+            t = t.contiguous()
+        else:
+            t = torch.full((rows,), float(timestep), device=dev, dtype=torch.float32)
+        c0 = self.config.block_out_channels[0]
+        t_emb = ops.timestep_embedding(t, self._freqs("t", c0), c0)
+        if timestep_cond is not None:
+            if self.cond_proj is None:
+                raise ValueError("timestep_cond given but the model has no time_cond_proj_dim")
+            cond = timestep_cond.to(device=dev, dtype=torch.float16).contiguous()
+            t_emb = ops.linear(cond, self.cond_proj, residual=t_emb)        # t_emb + cond_proj(w_emb)
+        h = ops.silu(ops.linear(t_emb, self.time_lin1.w, bias=self.time_lin1.b))
+        emb = ops.linear(h, self.time_lin2.w, bias=self.time_lin2.b)
+        if self.is_xl:
+            text_embeds = added["text_embeds"].to(device=dev, dtype=torch.float16)
+            time_ids = added["time_ids"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            d = self.config.addition_time_embed_dim
+            tid = ops.timestep_embedding(time_ids, self._freqs("t", d), d).reshape(rows, -1)
+            add_in = torch.cat([text_embeds, tid], dim=-1).contiguous()
+            h = ops.silu(ops.linear(add_in, self.add_lin1.w, bias=self.add_lin1.b))
+            emb = ops.linear(h, self.add_lin2.w, bias=self.add_lin2.b, residual=emb)   # emb + aug_emb
+        # every ResnetBlock2D consumes time_emb_proj(silu(emb)): one GEMM for all of them, fp32 out
+        return ops.linear(ops.silu(emb), self.temb_all.w, bias=self.temb_all.b, out_fp32=True)
+
+    # ------------------------------------------------------------------ blocks
+    def _res(self, r, x0, x1, B, H, W):
+        """ResnetBlock2D over channels-last tokens; (x0 | x1) is the virtual channel concat of the skip."""
+        ws = self._gn_ws
+        h = ops.groupnorm(x0, B, H * W, r.norm1.g, r.norm1.b, 1e-5, True, ws, x1=x1)
+        temb = self._temb[:, r.temb_off:r.temb_off + r.cout]
+        h = ops.conv3x3(h, r.conv1.w, B, H, W, bias=r.conv1.b, rowvec=temb)
+        h = ops.groupnorm(h, B, H * W, r.norm2.g, r.norm2.b, 1e-5, True, ws)
+        if r.shortcut is not None:
+            sc = ops.linear(x0, r.shortcut.w, bias=r.shortcut.b, a1=x1)
+        else:
+            sc = x0
+        return ops.conv3x3(h, r.conv2.w, B, H, W, bias=r.conv2.b, residual=sc)
+
+    def _attention(self, q, k, v, B, heads, Nq, Nk, d, is_cross, place):
+        """Attention core + the p2p controller protocol (utils/p2p.py:335-338)."""
+        scale = d ** -0.5
+        ctrl = self.controller
+        req = "none" if ctrl is None else ctrl.probs_request(is_cross, place, Nq, Nk)
+        if req == "none":
+            out = ops.attention(q, k, v, B, heads, Nq, Nk, d, scale)
+            if ctrl is not None:
+                ctrl.layer_skipped(is_cross, place)
+            return out
+        ldp = (Nk + 7) // 8 * 8
+        if req == "read" and Nk <= 128:
+            probs = torch.zeros((B * heads, Nq, ldp), device=q.device, dtype=torch.float16)
+            out = ops.attention(q, k, v, B, heads, Nq, Nk, d, scale, probs_out=probs)
+            ctrl.call_rows(probs[..., :Nk], is_cross, place, self._cond_only)
+            return out
+        # explicit probabilities: scores GEMM -> softmax -> controller (may edit in place) -> P.V GEMM
+        probs = torch.zeros((B * heads, Nq, ldp), device=q.device, dtype=torch.float16)
+        ops.attn_scores(q, k, B, heads, Nq, Nk, d, scale, probs)
+        ops.softmax_(probs, Nk)
+        view = probs[..., :Nk]
+        edited = ctrl.call_rows(view, is_cross, place, self._cond_only)
+        if edited.data_ptr() != view.data_ptr() or edited.stride() != view.stride():
+            view.copy_(edited)           # controller returned a new tensor: bring it back into the padded buffer
+        out = torch.empty((B * Nq, heads * d), device=q.device, dtype=torch.float16)
+        ops.attn_pv(probs, v, B, heads, Nq, Nk, d, out)
+        return out
+
+    def _tfm(self, t, x, ctx, B, HW, place):
+        C, heads, d = t.C, t.heads, t.d
+        n_ctx = ctx.shape[0] // B
+        h = ops.groupnorm(x, B, HW, t.norm.g, t.norm.b, 1e-6, False, self._gn_ws)
+        h = ops.linear(h, t.proj_in.w, bias=t.proj_in.b)
+        for blk in t.blocks:
+            n = ops.layernorm(h, blk.ln1.g, blk.ln1.b)
+            qkv = ops.linear(n, blk.qkv)
+            a = self._attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads, HW, HW, d, False, place)
+            h = ops.linear(a, blk.out1.w, bias=blk.out1.b, residual=h)
+            n = ops.layernorm(h, blk.ln2.g, blk.ln2.b)
+            q = ops.linear(n, blk.q2)
+            kv = ops.linear(ctx, blk.kv2)
+            a = self._attention(q, kv[:, :C], kv[:, C:], B, heads, HW, n_ctx, d, True, place)
+            h = ops.linear(a, blk.out2.w, bias=blk.out2.b, residual=h)
+            n = ops.layernorm(h, blk.ln3.g, blk.ln3.b)
+            gg = ops.linear(n, blk.ff1.w, bias=blk.ff1.b, geglu=True, force_bn=GEGLU_BN)
+            h = ops.linear(gg, blk.ff2.w, bias=blk.ff2.b, residual=h)
+        return ops.linear(h, t.proj_out.w, bias=t.proj_out.b, residual=x)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states=None, timestep_cond=None, added_cond_kwargs=None,
+                cross_attention_kwargs=None, return_dict=True, cond_only=False, update=None):
+        """sample: [rows, 4, H, W] (any float dtype; computed in fp16) -> eps fp32 [rows, 4, H, W].
+        `cond_only`: the rows are the conditional half only (controller sees them all).
+        `update`: optional (x_t fp32 NCHW, alpha_t, sigma_t, alpha_s, sigma_s): fuse predicted_origin into the
+        conv_out epilogue; the next latent is returned as out["next_sample"]."""
+        dev = self.device
+        rows, _, H, W = sample.shape
+        lat = sample.to(device=dev, dtype=torch.float32).contiguous()
+        ctx = encoder_hidden_states.to(device=dev, dtype=torch.float16)
+        if ctx.shape[0] != rows:
+            raise ValueError(f"encoder_hidden_states rows {ctx.shape[0]} != sample rows {rows}")
+        ctx = ctx.reshape(rows * ctx.shape[1], ctx.shape[2]).contiguous()
+        self._cond_only = cond_only
+        self._gn_ws = torch.empty(rows * 4096, device=dev, dtype=torch.float32)
+        self._temb = self._time_embed(rows, timestep, timestep_cond, added_cond_kwargs)
+
+        x = ops.conv3x3(ops.latent_to_nhwc(lat, cpad=8), self.conv_in.w, rows, H, W, bias=self.conv_in.b)
+        skips = [(x, H, W)]
+        for blk in self.down:
+            for j, r in enumerate(blk.resnets):
+                x = self._res(r, x, None, rows, H, W)
+                if blk.attns is not None:
+                    x = self._tfm(blk.attns[j], x, ctx, rows, H * W, "down")
+                skips.append((x, H, W))
+            if blk.down is not None:
+                x = ops.linear(ops.im2col_s2(x, rows, H, W), blk.down.w, bias=blk.down.b)
+                H, W = H // 2, W // 2
+                skips.append((x, H, W))
+        x = self._res(self.mid.res0, x, None, rows, H, W)
+        x = self._tfm(self.mid.attn, x, ctx, rows, H * W, "mid")
+        x = self._res(self.mid.res1, x, None, rows, H, W)
+        for blk in self.up:
+            for j, r in enumerate(blk.resnets):
+                skip, sh, sw = skips.pop()
+                assert (sh, sw) == (H, W)
+                x = self._res(r, x, skip, rows, H, W)
+                if blk.attns is not None:
+                    x = self._tfm(blk.attns[j], x, ctx, rows, H * W, "up")
+            if blk.up is not None:
+                x = ops.conv3x3(ops.upsample2x(x, rows, H, W), blk.up.w, rows, 2 * H, 2 * W, bias=blk.up.b)
+                H, W = 2 * H, 2 * W
+        x = ops.groupnorm(x, rows, H * W, self.norm_out.g, self.norm_out.b, 1e-5, True, self._gn_ws)
+        eps = torch.empty((rows, self.config.out_channels, H, W), device=dev, dtype=torch.float32)
+        nxt = None
+        if update is not None:
+            x_t, a_t, s_t, a_s, s_s = update
+            nxt = torch.empty_like(eps)
+            ops.conv3x3(x, self.conv_out.w, rows, H, W, bias=self.conv_out.b, nchw_out=eps,
+                        upd_x=x_t, upd_out=nxt, upd_coefs=(a_t, s_t, a_s, s_s))
+        else:
+            ops.conv3x3(x, self.conv_out.w, rows, H, W, bias=self.conv_out.b, nchw_out=eps)
+        self._temb = None
+        if not return_dict:
+            return (eps,) if nxt is None else (eps, nxt)
+        out = UNetOutput(sample=eps)
+        if nxt is not None:
+            out["next_sample"] = nxt
+        return out
+
+    __call__ = forward

@@ -23,7 +23,7 @@ def _rand(*shape, scale=1.0, seed=0):
 
 def _close(got, ref, rtol=1e-3, atol=2e-3, what=""):
     got = got.float()
-    ref = ref.float()
+    ref = ref.float().to(got.device)
     err = (got - ref).abs()
     tol = atol + rtol * ref.abs()
     bad = (err > tol).sum().item()
