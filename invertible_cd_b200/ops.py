@@ -11,6 +11,23 @@ import torch
 from . import _lib
 
 launch_count = 0  # number of kernel launches issued through this module (bench.py reports it)
+profile = None    # when a list: every tensor-core launch appends (kind, flops, start_event, end_event)
+
+
+def _prof_begin():
+    if profile is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(ev, kind, work):
+    if ev is None:
+        return
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    profile.append((kind, work, ev, end))
 
 
 def _stream():
@@ -39,8 +56,12 @@ def gemm_raw(**kw):
         if isinstance(v, torch.Tensor):
             v = v.data_ptr()
         setattr(g, k, v if v is not None else 0)
+    ev = _prof_begin()
     _lib.check(_lib.load().icd_gemm(C.byref(g), _stream()), "icd_gemm")
     _count()
+    if ev is not None:
+        k_total = g.K * (9 if g.a_mode == 1 else 1)
+        _prof_end(ev, "gemm_tc", 2.0 * g.M * g.N * k_total * g.Z)
 
 
 def pick_bn(M, N, Z=1, geglu=False, b_mn_major=False, force_bn=0):
@@ -121,11 +142,13 @@ def attention(q, k, v, B, H, Nq, Nk, D, scale, out=None, probs_out=None):
     _f16(q, "q"); _f16(k, "k"); _f16(v, "v")
     if out is None:
         out = torch.empty((B * Nq, H * D), device=q.device, dtype=torch.float16)
+    ev = _prof_begin()
     _lib.check(_lib.load().icd_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Nq, Nk, D, q.stride(0),
                                          k.stride(0), v.stride(0), out.stride(0), float(scale), _ptr(probs_out),
                                          probs_out.stride(1) if probs_out is not None else 0, _stream()),
                "icd_attention")
     _count()
+    _prof_end(ev, "attention_tc", 4.0 * B * H * Nq * Nk * D)
     return out
 
 
@@ -137,9 +160,11 @@ def groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=None, out=None, groups=3
         out = torch.empty((B * HW, C0 + C1), device=x0.device, dtype=torch.float16)
     if ws.numel() < B * 64 * 64:
         raise ValueError("groupnorm workspace too small (need B*4096 floats)")
+    ev = _prof_begin()
     _lib.check(_lib.load().icd_groupnorm(_ptr(x0), C0, _ptr(x1), C1, _ptr(out), B, HW, groups, float(eps),
                                          _ptr(gamma), _ptr(beta), int(silu), _ptr(ws), _stream()), "icd_groupnorm")
     _count(2)
+    _prof_end(ev, "groupnorm", 2.0 * B * HW * (C0 + C1) * 2)   # algorithmic bytes: read once + write once
     return out
 
 

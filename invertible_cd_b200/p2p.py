@@ -178,6 +178,11 @@ class SpatialReplace(EmptyControl):
 
 class AttentionStore(AttentionControl):
 
+    # Set to False to skip materialising the self-attention maps (N_q <= 32^2): nothing in the reference consumes
+    # them (LocalBlend reads five cross maps only, utils/p2p.py:35-37) and they are 11x the volume of the cross
+    # maps. Default True = reference behaviour (utils/p2p.py:145-149).
+    capture_self = True
+
     def __init__(self):
         super().__init__()
         self.step_store = self.get_empty_store()
@@ -212,6 +217,8 @@ class AttentionStore(AttentionControl):
     def probs_request(self, is_cross, place_in_unet, n_query, n_key):
         if type(self).forward is not AttentionStore.forward and not isinstance(self, AttentionControlEdit):
             return "edit"       # user subclass with its own forward: reference semantics
+        if not is_cross and not self.capture_self:
+            return "none"
         return "read" if n_query <= _STORE_MAX_QUERIES else "none"
 
 

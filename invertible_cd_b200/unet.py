@@ -187,6 +187,13 @@ class B200UNet:
             self._freq_cache[key] = f.to(self.device)
         return self._freq_cache[key]
 
+    def cached_vector(self, values):
+        """Small fp32 device vector, uploaded once per distinct value tuple (keeps the step free of H2D copies)."""
+        key = ("vec",) + tuple(float(v) for v in values)
+        if key not in self._freq_cache:
+            self._freq_cache[key] = torch.tensor([float(v) for v in values], dtype=torch.float32, device=self.device)
+        return self._freq_cache[key]
+
     def guidance_embedding(self, w, dim=512):
         """w: fp32 [rows] device tensor -> fp16 [rows, dim] (utils/generation.py:96-122)."""
         return ops.guidance_embedding(w, self._freqs("w", dim), dim)
