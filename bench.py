@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sd15", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step inside an NVTX range 'icd_step' (for ncu) and dump its launch shapes")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -258,6 +260,20 @@ def main():
         if gather and world > 1:
             out = dist_utils.gather_latents(out, n_total, B)
         return out
+
+    if args.profile_step:
+        for _ in range(2):
+            loop(static_lat, static_ctx)
+        torch.cuda.synchronize()
+        ops.shape_log = []
+        torch.cuda.nvtx.range_push("icd_step")
+        loop(static_lat, static_ctx)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"step_shapes_{args.workload}.json"), "w") as f:
+            json.dump(ops.shape_log, f)
+        return
 
     # eager warm-up (fills descriptor / constant caches), then count launches of one step
     for _ in range(2):

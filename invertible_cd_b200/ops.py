@@ -12,6 +12,7 @@ from . import _lib
 
 launch_count = 0  # number of kernel launches issued through this module (bench.py reports it)
 profile = None    # when a list: every tensor-core launch appends (kind, flops, start_event, end_event)
+shape_log = None  # when a list: every gemm / attention launch appends a dict describing its problem
 
 
 def _prof_begin():
@@ -56,6 +57,11 @@ def gemm_raw(**kw):
         if isinstance(v, torch.Tensor):
             v = v.data_ptr()
         setattr(g, k, v if v is not None else 0)
+    if shape_log is not None:
+        shape_log.append({"kind": "gemm_tc", "M": g.M, "N": g.N, "K": g.K * (9 if g.a_mode == 1 else 1), "Z": g.Z,
+                          "conv": g.a_mode, "geglu": g.geglu, "mn": g.b_mn_major,
+                          "bn": pick_bn(g.M, g.N, g.Z, bool(g.geglu), bool(g.b_mn_major), g.force_bn),
+                          "flops": 2.0 * g.M * g.N * g.K * (9 if g.a_mode == 1 else 1) * g.Z})
     ev = _prof_begin()
     _lib.check(_lib.load().icd_gemm(C.byref(g), _stream()), "icd_gemm")
     _count()
@@ -142,6 +148,9 @@ def attention(q, k, v, B, H, Nq, Nk, D, scale, out=None, probs_out=None):
     _f16(q, "q"); _f16(k, "k"); _f16(v, "v")
     if out is None:
         out = torch.empty((B * Nq, H * D), device=q.device, dtype=torch.float16)
+    if shape_log is not None:
+        shape_log.append({"kind": "attention_tc", "B": B, "H": H, "Nq": Nq, "Nk": Nk, "D": D,
+                          "probs": probs_out is not None, "flops": 4.0 * B * H * Nq * Nk * D})
     ev = _prof_begin()
     _lib.check(_lib.load().icd_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Nq, Nk, D, q.stride(0),
                                          k.stride(0), v.stride(0), out.stride(0), float(scale), _ptr(probs_out),
