@@ -27,7 +27,7 @@
 namespace icd {
 
 int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_b[3],
-                 const uint32_t box[4]);
+                 const uint32_t box[4], int swizzle_bytes);
 
 struct AttnParams {
   int B, H, Nq, Nk;
@@ -344,14 +344,14 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nq, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)q_ld * 2, (uint64_t)q_ld * Nq * 2};
-    if (make_tmap_4d(&tq, q, dims, str, box)) return 1;
+    if (make_tmap_4d(&tq, q, dims, str, box, 128)) return 1;
   }
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nk, (uint64_t)B};
     const uint64_t strk[3] = {(uint64_t)D * 2, (uint64_t)k_ld * 2, (uint64_t)k_ld * Nk * 2};
-    if (make_tmap_4d(&tk, k, dims, strk, box)) return 1;
+    if (make_tmap_4d(&tk, k, dims, strk, box, 128)) return 1;
     const uint64_t strv[3] = {(uint64_t)D * 2, (uint64_t)v_ld * 2, (uint64_t)v_ld * Nk * 2};
-    if (make_tmap_4d(&tv, v, dims, strv, box)) return 1;
+    if (make_tmap_4d(&tv, v, dims, strv, box, 128)) return 1;
   }
   AttnParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;

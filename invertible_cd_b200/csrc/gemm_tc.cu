@@ -50,15 +50,15 @@ struct TmapKeyHash {
 static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
 static std::mutex g_tmap_mu;
 
-// fp16, rank-4, 128B swizzle. dims/box in elements, strides (dims 1..3) in bytes.
+// fp16, rank-4, 128B (or 64B) swizzle. dims/box in elements, strides (dims 1..3) in bytes.
 int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_b[3],
-                 const uint32_t box[4]) {
+                 const uint32_t box[4], int swizzle_bytes) {
   TmapKey key;
   key.v[0] = reinterpret_cast<uint64_t>(ptr);
   for (int i = 0; i < 4; ++i) key.v[1 + i] = dims[i];
   for (int i = 0; i < 3; ++i) key.v[5 + i] = strides_b[i];
   for (int i = 0; i < 4; ++i) key.v[8 + i] = box[i];
-  key.v[12] = 0;
+  key.v[12] = static_cast<uint64_t>(swizzle_bytes);
   {
     std::lock_guard<std::mutex> lk(g_tmap_mu);
     auto it = g_tmap_cache.find(key);
@@ -78,7 +78,9 @@ int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], cons
   cuuint32_t es[4] = {1, 1, 1, 1};
   alignas(64) CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[512];
@@ -124,8 +126,8 @@ static int pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn)
 }
 
 template <int BN>
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                  const CUtensorMap& r, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -137,7 +139,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   const long long tiles = static_cast<long long>((p.M + 127) / 128) * ((p.N + BN - 1) / BN) * p.Z;
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, p);
+  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, o, r, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return 0;
@@ -197,12 +199,12 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     {
       const uint64_t dims[4] = {(uint64_t)g->K0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       const uint64_t str[3] = {(uint64_t)g->a0_ld * 2, (uint64_t)g->a0_ld * W * 2, (uint64_t)g->a0_ld * hw * 2};
-      if (make_tmap_4d(&tmA0, g->a0, dims, str, box)) return 1;
+      if (make_tmap_4d(&tmA0, g->a0, dims, str, box, 128)) return 1;
     }
     if (g->a1 != nullptr) {
       const uint64_t dims[4] = {(uint64_t)g->K1, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       const uint64_t str[3] = {(uint64_t)g->a1_ld * 2, (uint64_t)g->a1_ld * W * 2, (uint64_t)g->a1_ld * hw * 2};
-      if (make_tmap_4d(&tmA1, g->a1, dims, str, box)) return 1;
+      if (make_tmap_4d(&tmA1, g->a1, dims, str, box, 128)) return 1;
     } else {
       tmA1 = tmA0;
     }
@@ -215,14 +217,14 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
       const uint64_t s1 = g->a_z1_stride > 0 ? (uint64_t)g->a_z1_stride * 2 : (uint64_t)g->a0_ld * 2;
       const uint64_t s2 = g->a_z2_stride > 0 ? (uint64_t)g->a_z2_stride * 2 : s1;
       const uint64_t str[3] = {(uint64_t)g->a0_ld * 2, s1, s2};
-      if (make_tmap_4d(&tmA0, g->a0, dims, str, box)) return 1;
+      if (make_tmap_4d(&tmA0, g->a0, dims, str, box, 128)) return 1;
     }
     if (g->a1 != nullptr) {
       const uint64_t dims[4] = {(uint64_t)g->K1, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
       const uint64_t s1 = g->a_z1_stride > 0 ? (uint64_t)g->a_z1_stride * 2 : (uint64_t)g->a1_ld * 2;
       const uint64_t s2 = g->a_z2_stride > 0 ? (uint64_t)g->a_z2_stride * 2 : s1;
       const uint64_t str[3] = {(uint64_t)g->a1_ld * 2, s1, s2};
-      if (make_tmap_4d(&tmA1, g->a1, dims, str, box)) return 1;
+      if (make_tmap_4d(&tmA1, g->a1, dims, str, box, 128)) return 1;
     } else {
       tmA1 = tmA0;
     }
@@ -239,11 +241,11 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     if (g->b_mn_major) {
       const uint64_t dims[4] = {(uint64_t)g->N, kreal, batched_b ? (uint64_t)p.ZB1 : 1, batched_b ? z2 : 1};
       const uint32_t box[4] = {64, 64, 1, 1};
-      if (make_tmap_4d(&tmB, g->b, dims, str, box)) return 1;
+      if (make_tmap_4d(&tmB, g->b, dims, str, box, 128)) return 1;
     } else {
       const uint64_t dims[4] = {kreal, (uint64_t)g->N, batched_b ? (uint64_t)p.ZB1 : 1, batched_b ? z2 : 1};
       const uint32_t box[4] = {64, (uint32_t)bn, 1, 1};
-      if (make_tmap_4d(&tmB, g->b, dims, str, box)) return 1;
+      if (make_tmap_4d(&tmB, g->b, dims, str, box, 128)) return 1;
     }
     p.b_batched = batched_b ? 1 : 0;
   }
@@ -270,11 +272,36 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   if (p.upd_x != nullptr && !(p.out_fp32 && p.out_mode == GEMM_OUT_TRANSPOSED))
     return set_error("icd_gemm: fused update needs fp32 transposed output");
 
+  // staged TMA-store epilogue whenever the output is an fp16 row-major matrix TMA can address
+  CUtensorMap tmOut = tmB, tmRes = tmB;
+  const bool aligned = (g->ldc % 8) == 0 && (reinterpret_cast<uint64_t>(g->out) & 15) == 0 &&
+                       (g->out_z1_stride % 8) == 0 && (g->out_z2_stride % 8) == 0;
+  const bool res_ok = g->residual == nullptr ||
+                      ((g->ldr % 8) == 0 && (reinterpret_cast<uint64_t>(g->residual) & 15) == 0 && g->Z == 1);
+  p.epi_tma = (!g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR && aligned && res_ok) ? 1 : 0;
+  if (g->geglu && !p.epi_tma) return set_error("icd_gemm: GEGLU needs an aligned fp16 row-major output");
+  if (p.epi_tma) {
+    const uint64_t n_out = (uint64_t)(g->geglu ? g->N / 2 : g->N);
+    const uint64_t z2 = (uint64_t)((g->Z + p.ZA1 - 1) / p.ZA1);
+    const uint32_t box[4] = {32, 128, 1, 1};
+    const uint64_t dims[4] = {n_out, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
+    const uint64_t s1 = g->out_z1_stride > 0 ? (uint64_t)g->out_z1_stride * 2 : (uint64_t)g->ldc * 2;
+    const uint64_t s2 = g->out_z2_stride > 0 ? (uint64_t)g->out_z2_stride * 2 : s1;
+    const uint64_t str[3] = {(uint64_t)g->ldc * 2, s1, s2};
+    if (make_tmap_4d(&tmOut, g->out, dims, str, box, 64)) return 1;
+    if (g->residual != nullptr) {
+      const uint64_t rdims[4] = {n_out, (uint64_t)g->M, 1, 1};
+      const uint64_t rstr[3] = {(uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2};
+      if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, box, 64)) return 1;
+      p.res_tma = 1;
+    }
+  }
+
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 64: return launch<64>(tmA0, tmA1, tmB, p, st);
-    case 128: return launch<128>(tmA0, tmA1, tmB, p, st);
-    case 160: return launch<160>(tmA0, tmA1, tmB, p, st);
-    default: return launch<256>(tmA0, tmA1, tmB, p, st);
+    case 64: return launch<64>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
+    case 128: return launch<128>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
+    case 160: return launch<160>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
+    default: return launch<256>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
   }
 }

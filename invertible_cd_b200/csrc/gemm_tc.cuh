@@ -49,6 +49,9 @@ struct GemmParams {
   int out_fp32;
   int out_mode;           // GEMM_OUT_ROWMAJOR | GEMM_OUT_TRANSPOSED
   int geglu;              // out[:, j] = h_j * gelu(g_j); B rows are packed per N tile as [BN/2 h | BN/2 g]
+  int epi_tma;            // 1: fp16 row-major output staged in smem (64B swizzle) and written with TMA stores;
+                          //    the residual tile is prefetched into the same staging buffer by TMA
+  int res_tma;            // residual present (epi_tma mode)
   // fused consistency update (predicted_origin, utils/generation.py:136-155) on the conv_out tile:
   //   x_s = alpha_s * (x_t - sigma_t*eps) / alpha_t + sigma_s * eps      (same layout as the transposed output)
   const float* upd_x;     // current latent x_t (fp32, NCHW) or null
@@ -62,29 +65,35 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int C_BYTES = 4 * 8192;  // epilogue staging: 4 atoms of [128 rows x 32 cols] fp16, 64B swizzle
+  static constexpr int BUDGET = 232448 - 1024 - 256 - C_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;                            // power of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = 192;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_c = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + Cfg::C_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* cbuf_free = bars + 2 * STAGES + 4;   // staging buffer reusable (previous TMA stores have read it)
+  uint64_t* res_full = bars + 2 * STAGES + 5;    // residual tile landed in the staging buffer
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,6 +110,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 128);
     }
+    mbar_init(cbuf_free, 1);
+    mbar_init(res_full, 1);
+    tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmRes);
     fence_mbar_init();
   } else if (warp == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -205,6 +218,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
     int iter = 0;
+    if (p.epi_tma) {
+      // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual, GEGLU) -> swizzled smem -> TMA store
+      constexpr int OUTW = BN;                    // accumulator columns; GEGLU emits OUTW/2 output columns
+      const int outw = p.geglu ? OUTW / 2 : OUTW; // output columns per tile
+      const int n_out_total = p.geglu ? p.N / 2 : p.N;
+      const int passes = (outw + 127) / 128;      // staging holds 128 output columns
+      const bool leader = (warp == 2 && lane == 0);
+      const uint32_t stg = smem_u32(smem_c);
+      const uint32_t sw = (row_in_tile >> 1) & 3; // 64B swizzle: 16B-chunk index ^= (row / 2) % 4
+      uint32_t unit = 0;                          // (tile, pass) counter -> barrier parity
+      // residual prefetch for the first unit
+      auto issue_residual = [&](int tile_i, int pass_i) {
+        const int z_i = tile_i / tiles_per_z;
+        const int t_i = tile_i - z_i * tiles_per_z;
+        const int mt_i = t_i / n_tiles, nt_i = t_i - mt_i * n_tiles;
+        const int cols = min(128, outw - pass_i * 128);
+        const int natoms = (cols + 31) / 32;
+        mbar_expect_tx(res_full, natoms * 8192);
+        for (int a = 0; a < natoms; ++a)
+          tma_load_4d(smem_c + a * 8192, &tmRes, res_full, nt_i * outw + pass_i * 128 + a * 32, mt_i * 128,
+                      z_i % p.ZA1, z_i / p.ZA1);
+      };
+      if (p.res_tma && leader && blockIdx.x < total_tiles) issue_residual(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int z = tile / tiles_per_z;
+        const int t = tile - z * tiles_per_z;
+        const int mt = t / n_tiles, nt = t - mt * n_tiles;
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
+        const int row = mt * 128 + row_in_tile;
+        const int img = min(row, p.M - 1) / p.rows_per_img;
+        const float* rv = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
+        const int n_out0 = nt * outw;
+        for (int pass = 0; pass < passes; ++pass, ++unit) {
+          if (p.res_tma)
+            mbar_wait(res_full, unit & 1);
+          else
+            mbar_wait(cbuf_free, (unit & 1) ^ 1);
+          const int pass_cols = min(128, outw - pass * 128);
+#pragma unroll 1
+          for (int c0 = 0; c0 < pass_cols; c0 += 32) {
+            const int col_t = pass * 128 + c0;     // output column within the tile
+            const int ncol = n_out0 + col_t;       // global output column
+            if (ncol >= n_out_total) break;        // warp-uniform
+            float v[32];
+            if (p.geglu) {
+              float gt[32];
+              tmem_ld32(t_addr + col_t, v);
+              tmem_ld32(t_addr + OUTW / 2 + col_t, gt);
+              tmem_ld_wait();
+              const int nb = nt * BN + col_t;      // packed bias index of the hidden half
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float hv = v[j] * p.alpha, gv = gt[j] * p.alpha;
+                if (p.bias != nullptr) {
+                  hv += __ldg(p.bias + nb + j);
+                  gv += __ldg(p.bias + nb + OUTW / 2 + j);
+                }
+                v[j] = hv * gelu_erf(gv);
+              }
+            } else {
+              tmem_ld32(t_addr + col_t, v);
+              tmem_ld_wait();
+              const bool full = ncol + 32 <= n_out_total;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = v[j] * p.alpha;
+                if (full || ncol + j < n_out_total) {
+                  if (p.bias != nullptr) x += __ldg(p.bias + ncol + j);
+                  if (rv != nullptr) x += __ldg(rv + ncol + j);
+                }
+                v[j] = x;
+              }
+            }
+            const uint32_t atom = stg + (c0 >> 5) * 8192 + row_in_tile * 64;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const uint32_t addr = atom + ((cc ^ sw) << 4);
+              if (p.res_tma) {
+                uint32_t r0, r1, r2, r3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                             : "r"(addr));
+                const uint32_t rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[q]));
+                  v[cc * 8 + 2 * q] += f.x;
+                  v[cc * 8 + 2 * q + 1] += f.y;
+                }
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q], v[cc * 8 + 2 * q + 1]);
+                o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                           "r"(o[3])
+                           : "memory");
+            }
+          }
+          if (pass == passes - 1) {   // all TMEM reads of this accumulator are done
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            const int natoms = (pass_cols + 31) / 32;
+            for (int a = 0; a < natoms; ++a) {
+              const int ncol = n_out0 + pass * 128 + a * 32;
+              if (ncol < n_out_total)
+                tma_store_4d(&tmOut, smem_c + a * 8192, ncol, mt * 128, z % p.ZA1, z / p.ZA1);
+            }
+            bulk_commit();
+            bulk_wait_read0();
+            // hand the staging buffer to the next unit: prefetch its residual, or just mark it free
+            if (p.res_tma) {
+              int nt_tile = tile, npass = pass + 1;
+              if (npass == passes) { npass = 0; nt_tile = tile + gridDim.x; }
+              if (nt_tile < total_tiles) issue_residual(nt_tile, npass);
+            } else {
+              mbar_arrive(cbuf_free);
+            }
+          }
+        }
+      }
+      if (leader) bulk_wait0();
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int z = tile / tiles_per_z;
       const int t = tile - z * tiles_per_z;
