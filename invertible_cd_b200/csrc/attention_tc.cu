@@ -46,7 +46,7 @@ struct AttnCfg {
   static constexpr int TILE_BYTES = DATOMS * 16384;  // one Q / K / V tile of 128 rows
   static constexpr int P_BYTES = 2 * 16384;          // 128 x 128 fp16 probabilities
   static constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES + 256;
-  static constexpr int TMEM_COLS = (128 + DP) <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = (128 + DP + 16) <= 256 ? 256 : 512;   // S | O | 16 row-sum columns
   static constexpr int MIN_CTAS = (DATOMS == 1) ? 2 : 1;
 };
 
@@ -70,6 +70,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_full = s_full + 1;
   uint64_t* o_full = s_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 3);
+  uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars) + 128;   // one 8x8 fp16 core matrix of 1.0 (128 B)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = (p.Nq + 127) / 128;
@@ -95,6 +96,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_mbar_init();
   } else if (warp == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  } else if (warp == 2) {
+    reinterpret_cast<uint32_t*>(s_ones)[lane] = 0x3C003C00u;   // 64 halves of 1.0
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -102,6 +106,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_L = tmem_O + DP;       // row sums: L = P . 1 accumulated by the tensor core
 
   if (warp == 0) {
     if (lane == 0) {
@@ -127,6 +132,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, DP, false, true);
+      constexpr uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);
       mbar_wait(q_full, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -161,9 +167,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t pa = smem_u32(sP), va = smem_u32(sV + stage * Cfg::TILE_BYTES);
           const int valid = min(128, p.Nk - j * 128);
           const int ksteps = (valid + 15) / 16;
+          // row sums ride on the tensor core: L[128x16] += P[128xK] . ones[Kx16] (every column = sum_k P)
+          // ones operand = a single no-swizzle 8x8 core matrix reused for every (row group, k chunk): LBO=SBO=0
+          const uint64_t ones_desc = (static_cast<uint64_t>((smem_u32(s_ones) >> 4) & 0x3FFF)) |
+                                     (static_cast<uint64_t>(1) << 46);
           for (int ks = 0; ks < ksteps; ++ks) {
-            umma_f16_ss(tmem_O, umma_smem_desc(pa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                        umma_smem_desc(va + ks * 2048, 16384, 1024), idesc_o, (j | ks) != 0);
+            const uint64_t pdesc = umma_smem_desc(pa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+            umma_f16_ss(tmem_O, pdesc, umma_smem_desc(va + ks * 2048, 16384, 1024), idesc_o, (j | ks) != 0);
+            umma_f16_ss(tmem_L, pdesc, ones_desc, idesc_l, (j | ks) != 0);
           }
         }
         umma_commit(&kv_empty[stage]);
@@ -177,70 +188,95 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int row = quad * 32 + lane;       // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int q = q0 + row;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY;
     const uint32_t p_row = smem_u32(sP) + row * 128;
     const int sw = row & 7;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int valid = min(128, p.Nk - j * 128);
-      // pass 1: row maximum
+      const bool partial = valid < 128;          // warp-uniform: only the last K/V tile can be partial
+      // pass 1: row maximum (S is re-read from TMEM in pass 2: keeps registers low for 2 CTAs/SM).
+      // TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is reduced.
+      const int nchunks = (valid + 31) >> 5;
       float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        if (c0 >= valid) break;
-        float s[32];
-        tmem_ld32(tmem_S + lane_off + c0, s);
-        tmem_ld_wait();
+      {
+        float sa[32], sb[32];
+        tmem_ld32(tmem_S + lane_off, sa);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < valid) m_tile = fmaxf(m_tile, s[i]);
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunks) {
+            float* cur = (c & 1) ? sb : sa;
+            float* nxt = (c & 1) ? sa : sb;
+            tmem_ld_wait();
+            if (c + 1 < nchunks) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, nxt);
+            if (partial) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= valid) cur[i] = -INFINITY;
+            }
+            float m0 = fmaxf(cur[0], cur[1]), m1 = fmaxf(cur[2], cur[3]);
+#pragma unroll
+            for (int i = 4; i < 32; i += 4) {
+              m0 = fmaxf(m0, fmaxf(cur[i], cur[i + 1]));
+              m1 = fmaxf(m1, fmaxf(cur[i + 2], cur[i + 3]));
+            }
+            m_tile = fmaxf(m_tile, fmaxf(m0, m1));
+          }
+        }
       }
       const float m_new = fmaxf(m_run, m_tile);
       const float m_scaled = m_new * p.scale_log2e;
       const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // 0 on the first tile (m_run = -inf)
-      // pass 2: probabilities -> swizzled smem (fp16), row sum
-      float l_tile = 0.f;
-      if (j > 0) mbar_wait(o_full, (j - 1) & 1);  // previous P.V finished: P smem and O are ours again
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t packed[16];
-        if (c0 < valid) {
-          float s[32];
-          tmem_ld32(tmem_S + lane_off + c0, s);
-          tmem_ld_wait();
+      // pass 2: p = exp2(s*scale*log2e - m) (one FFMA + one MUFU.EX2 per element, packed to fp16 pairs)
+      {
+        float sa[32], sb[32];
+        tmem_ld32(tmem_S + lane_off, sa);
+        if (j > 0) mbar_wait(o_full, (j - 1) & 1);  // previous P.V finished: P smem and O are ours again
+        tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float e0 = (c0 + i < valid) ? exp2f(s[i] * p.scale_log2e - m_scaled) : 0.f;
-            float e1 = (c0 + i + 1 < valid) ? exp2f(s[i + 1] * p.scale_log2e - m_scaled) : 0.f;
-            const __half2 hh = __floats2half2_rn(e0, e1);
-            // accumulate what the tensor core will actually see (fp16-rounded), keeps P.V / l consistent
-            const float2 back = __half22float2(hh);
-            l_tile += back.x + back.y;
-            packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t packed[16];
+          if (c < nchunks) {
+            float* cur = (c & 1) ? sb : sa;
+            float* nxt = (c & 1) ? sa : sb;
+            tmem_ld_wait();
+            if (c + 1 < nchunks) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, nxt);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float x0 = fmaf(cur[i], p.scale_log2e, -m_scaled);
+              float x1 = fmaf(cur[i + 1], p.scale_log2e, -m_scaled);
+              if (partial) {
+                if (c * 32 + i >= valid) x0 = -INFINITY;
+                if (c * 32 + i + 1 >= valid) x1 = -INFINITY;
+              }
+              float e0, e1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+              const __half2 e = __floats2half2_rn(e0, e1);
+              packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&e);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = 0u;
           }
-        } else {
+          const uint32_t atom_base = p_row + (c >> 1) * 16384;
+          const int chunk0 = (c & 1) * 4;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = 0u;
-        }
-        // 32 columns = 4 x 16-byte chunks; chunk index within the 64-wide atom is XOR-swizzled with (row & 7)
-        const uint32_t atom_base = p_row + (c0 >> 6) * 16384;
-        const int chunk0 = (c0 & 63) >> 3;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const uint32_t addr = atom_base + (((chunk0 + cc) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * cc]),
-                       "r"(packed[4 * cc + 1]), "r"(packed[4 * cc + 2]), "r"(packed[4 * cc + 3])
-                       : "memory");
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t addr = atom_base + (((chunk0 + cc) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * cc]),
+                         "r"(packed[4 * cc + 1]), "r"(packed[4 * cc + 2]), "r"(packed[4 * cc + 3])
+                         : "memory");
+          }
         }
       }
-      // rescale the running output if any row maximum of this warp moved
+      // rescale the running output and row sums if any row maximum of this warp moved
       if (j > 0) {
         const bool need = alpha != 1.0f;
         if (__any_sync(0xffffffffu, need)) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < DP; c0 += 16) {
+          for (int c0 = 0; c0 < DP + 16; c0 += 16) {
             float o[16];
             tmem_ld16(tmem_O + lane_off + c0, o);
             tmem_ld_wait();
@@ -257,27 +293,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_st_wait();
         }
       }
-      l_run = l_run * alpha + l_tile;
       m_run = m_new;
-      // single-tile case: emit normalised probabilities (AttentionStore capture)
-      if (p.probs != nullptr && n_kv == 1 && q < p.Nq) {
-        const float inv = 1.f / l_run;
-        __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
-        for (int c = 0; c < valid; ++c) {
-          const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2;
-          unsigned short u;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
-          pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * inv);
-        }
-      }
       fence_proxy_async_smem();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // epilogue: O / l -> fp16 -> global
+    // epilogue: O / l -> fp16 -> global   (l = row sum accumulated by the ones-MMA)
     mbar_wait(o_full, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv = 1.f / l_run;
+    float inv;
+    {
+      float l16[16];
+      tmem_ld16(tmem_L + lane_off, l16);
+      tmem_ld_wait();
+      inv = 1.f / l16[0];
+    }
+    if (p.probs != nullptr && n_kv == 1 && q < p.Nq) {
+      // single K/V tile: emit the normalised probabilities (AttentionStore capture) from the P tile in smem
+      __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
+      const int valid = p.Nk;
+      for (int c = 0; c + 1 < valid; c += 2) {
+        const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2;
+        uint32_t u;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(addr));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        *reinterpret_cast<__half2*>(pr + c) = __floats2half2_rn(f.x * inv, f.y * inv);
+      }
+      if (valid & 1) {
+        const int c = valid - 1;
+        const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2;
+        unsigned short u;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
+        pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * inv);
+      }
+    }
     __half* orow = p.out + (static_cast<long long>(b) * p.Nq + q) * p.out_ld + h * D;
 #pragma unroll 1
     for (int c0 = 0; c0 < DP; c0 += 16) {
