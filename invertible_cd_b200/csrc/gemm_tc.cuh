@@ -219,133 +219,149 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int row_in_tile = quad * 32 + lane;
     int iter = 0;
     if (p.epi_tma) {
-      // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual, GEGLU) -> swizzled smem -> TMA store
+      // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual, GEGLU) -> swizzled smem -> TMA store.
+      // Output is produced in 64-column units through a double-buffered staging area (2 x [128 rows x 64 cols],
+      // as 32-column atoms with 64B swizzle), so the TMA store of unit u overlaps the math of unit u+1.
+      // The residual rows are prefetched straight from global memory into registers BEFORE waiting for the
+      // accumulator, i.e. their latency hides behind the tile's main loop.
       constexpr int OUTW = BN;                    // accumulator columns; GEGLU emits OUTW/2 output columns
+      constexpr int RES_CHUNKS = (BN + 7) / 8;    // 16-byte residual chunks per row
       const int outw = p.geglu ? OUTW / 2 : OUTW; // output columns per tile
       const int n_out_total = p.geglu ? p.N / 2 : p.N;
-      const int passes = (outw + 127) / 128;      // staging holds 128 output columns
+      const int units = (outw + 63) / 64;
       const bool leader = (warp == 2 && lane == 0);
       const uint32_t stg = smem_u32(smem_c);
       const uint32_t sw = (row_in_tile >> 1) & 3; // 64B swizzle: 16B-chunk index ^= (row / 2) % 4
-      uint32_t unit = 0;                          // (tile, pass) counter -> barrier parity
-      // residual prefetch for the first unit
-      auto issue_residual = [&](int tile_i, int pass_i) {
-        const int z_i = tile_i / tiles_per_z;
-        const int t_i = tile_i - z_i * tiles_per_z;
-        const int mt_i = t_i / n_tiles, nt_i = t_i - mt_i * n_tiles;
-        const int cols = min(128, outw - pass_i * 128);
-        const int natoms = (cols + 31) / 32;
-        mbar_expect_tx(res_full, natoms * 8192);
-        for (int a = 0; a < natoms; ++a)
-          tma_load_4d(smem_c + a * 8192, &tmRes, res_full, nt_i * outw + pass_i * 128 + a * 32, mt_i * 128,
-                      z_i % p.ZA1, z_i / p.ZA1);
-      };
-      if (p.res_tma && leader && blockIdx.x < total_tiles) issue_residual(blockIdx.x, 0);
+      uint32_t unit = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         const int z = tile / tiles_per_z;
         const int t = tile - z * tiles_per_z;
         const int mt = t / n_tiles, nt = t - mt * n_tiles;
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
+        const int row = mt * 128 + row_in_tile;
+        const int n_out0 = nt * outw;
+        // residual prefetch (global -> registers), issued while the MMAs of this tile are still running
+        uint4 resv[RES_CHUNKS];
+        if (p.res_tma) {
+          const bool row_ok = row < p.M;
+          const __half* rp = p.residual + static_cast<long long>(row) * p.ldr + n_out0;
+#pragma unroll
+          for (int i = 0; i < RES_CHUNKS; ++i) {
+            resv[i] = make_uint4(0, 0, 0, 0);
+            if (row_ok && n_out0 + i * 8 < n_out_total) resv[i] = __ldg(reinterpret_cast<const uint4*>(rp + i * 8));
+          }
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
-        const int row = mt * 128 + row_in_tile;
         const int img = min(row, p.M - 1) / p.rows_per_img;
         const float* rv = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
-        const int n_out0 = nt * outw;
-        for (int pass = 0; pass < passes; ++pass, ++unit) {
-          if (p.res_tma)
-            mbar_wait(res_full, unit & 1);
-          else
-            mbar_wait(cbuf_free, (unit & 1) ^ 1);
-          const int pass_cols = min(128, outw - pass * 128);
-#pragma unroll 1
-          for (int c0 = 0; c0 < pass_cols; c0 += 32) {
-            const int col_t = pass * 128 + c0;     // output column within the tile
-            const int ncol = n_out0 + col_t;       // global output column
-            if (ncol >= n_out_total) break;        // warp-uniform
-            float v[32];
-            if (p.geglu) {
-              float gt[32];
-              tmem_ld32(t_addr + col_t, v);
-              tmem_ld32(t_addr + OUTW / 2 + col_t, gt);
-              tmem_ld_wait();
-              const int nb = nt * BN + col_t;      // packed bias index of the hidden half
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float hv = v[j] * p.alpha, gv = gt[j] * p.alpha;
-                if (p.bias != nullptr) {
-                  hv += __ldg(p.bias + nb + j);
-                  gv += __ldg(p.bias + nb + OUTW / 2 + j);
+        for (int u = 0; u < (OUTW + 63) / 64; ++u) {
+          if (u < units) {
+            const int unit_cols = min(64, outw - u * 64);
+            const uint32_t buf = stg + (unit & 1) * 16384;
+            // staging buffer (unit & 1) was last used by unit-2: its TMA store must have finished reading smem
+            if (leader) bulk_wait_read1();
+            named_bar_sync(1, 128);
+#pragma unroll
+            for (int h32 = 0; h32 < 2; ++h32) {
+              const int c0 = h32 * 32;
+              const int col_t = u * 64 + c0;         // output column within the tile
+              const int ncol = n_out0 + col_t;       // global output column
+              if (c0 < unit_cols && ncol < n_out_total) {   // warp-uniform
+                float v[32];
+                if (p.geglu) {
+                  float gt[32];
+                  tmem_ld32(t_addr + col_t, v);
+                  tmem_ld32(t_addr + OUTW / 2 + col_t, gt);
+                  tmem_ld_wait();
+                  const float4* bh = reinterpret_cast<const float4*>(p.bias + nt * BN + col_t);
+                  const float4* bg = reinterpret_cast<const float4*>(p.bias + nt * BN + OUTW / 2 + col_t);
+#pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    if (p.bias != nullptr) { b0 = __ldg(bh + j4); b1 = __ldg(bg + j4); }
+                    const float hb[4] = {b0.x, b0.y, b0.z, b0.w}, gb[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const int j = j4 * 4 + q;
+                      v[j] = (v[j] * p.alpha + hb[q]) * gelu_erf(gt[j] * p.alpha + gb[q]);
+                    }
+                  }
+                } else {
+                  tmem_ld32(t_addr + col_t, v);
+                  tmem_ld_wait();
+                  if (ncol + 32 <= n_out_total && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias + ncol) & 15) == 0) &&
+                      (rv == nullptr || (reinterpret_cast<uintptr_t>(rv + ncol) & 15) == 0)) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                      if (p.bias != nullptr) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + j4);
+                      if (rv != nullptr) b1 = __ldg(reinterpret_cast<const float4*>(rv + ncol) + j4);
+                      v[j4 * 4 + 0] = v[j4 * 4 + 0] * p.alpha + (b0.x + b1.x);
+                      v[j4 * 4 + 1] = v[j4 * 4 + 1] * p.alpha + (b0.y + b1.y);
+                      v[j4 * 4 + 2] = v[j4 * 4 + 2] * p.alpha + (b0.z + b1.z);
+                      v[j4 * 4 + 3] = v[j4 * 4 + 3] * p.alpha + (b0.w + b1.w);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                      float x = v[j] * p.alpha;
+                      if (ncol + j < n_out_total) {
+                        if (p.bias != nullptr) x += __ldg(p.bias + ncol + j);
+                        if (rv != nullptr) x += __ldg(rv + ncol + j);
+                      }
+                      v[j] = x;
+                    }
+                  }
                 }
-                v[j] = hv * gelu_erf(gv);
-              }
-            } else {
-              tmem_ld32(t_addr + col_t, v);
-              tmem_ld_wait();
-              const bool full = ncol + 32 <= n_out_total;
+                const uint32_t atom = buf + h32 * 8192 + row_in_tile * 64;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float x = v[j] * p.alpha;
-                if (full || ncol + j < n_out_total) {
-                  if (p.bias != nullptr) x += __ldg(p.bias + ncol + j);
-                  if (rv != nullptr) x += __ldg(rv + ncol + j);
-                }
-                v[j] = x;
-              }
-            }
-            const uint32_t atom = stg + (c0 >> 5) * 8192 + row_in_tile * 64;
+                for (int cc = 0; cc < 4; ++cc) {
+                  if (p.res_tma) {
+                    const int ci = (col_t >> 3) + cc;
+                    if (ci < RES_CHUNKS) {
+                      const uint4 rr = resv[ci];
+                      const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const uint32_t addr = atom + ((cc ^ sw) << 4);
-              if (p.res_tma) {
-                uint32_t r0, r1, r2, r3;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                             : "r"(addr));
-                const uint32_t rr[4] = {r0, r1, r2, r3};
+                      for (int q = 0; q < 4; ++q) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[q]));
+                        v[cc * 8 + 2 * q] += f.x;
+                        v[cc * 8 + 2 * q + 1] += f.y;
+                      }
+                    }
+                  }
+                  uint32_t o[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[q]));
-                  v[cc * 8 + 2 * q] += f.x;
-                  v[cc * 8 + 2 * q + 1] += f.y;
+                  for (int q = 0; q < 4; ++q) {
+                    const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q], v[cc * 8 + 2 * q + 1]);
+                    o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + ((cc ^ sw) << 4)), "r"(o[0]),
+                               "r"(o[1]), "r"(o[2]), "r"(o[3])
+                               : "memory");
                 }
               }
-              uint32_t o[4];
+            }
+            if (u == units - 1) {   // all TMEM reads of this accumulator are done
+              tc_fence_before();
+              mbar_arrive(&tmem_empty[acc]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, 128);
+            if (leader) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q], v[cc * 8 + 2 * q + 1]);
-                o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+              for (int h32 = 0; h32 < 2; ++h32) {
+                const int ncol = n_out0 + u * 64 + h32 * 32;
+                if (h32 * 32 < unit_cols && ncol < n_out_total)
+                  tma_store_4d(&tmOut, smem_c + (unit & 1) * 16384 + h32 * 8192, ncol, mt * 128, z % p.ZA1,
+                               z / p.ZA1);
               }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]),
-                           "r"(o[3])
-                           : "memory");
+              bulk_commit();
             }
-          }
-          if (pass == passes - 1) {   // all TMEM reads of this accumulator are done
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (leader) {
-            const int natoms = (pass_cols + 31) / 32;
-            for (int a = 0; a < natoms; ++a) {
-              const int ncol = n_out0 + pass * 128 + a * 32;
-              if (ncol < n_out_total)
-                tma_store_4d(&tmOut, smem_c + a * 8192, ncol, mt * 128, z % p.ZA1, z / p.ZA1);
-            }
-            bulk_commit();
-            bulk_wait_read0();
-            // hand the staging buffer to the next unit: prefetch its residual, or just mark it free
-            if (p.res_tma) {
-              int nt_tile = tile, npass = pass + 1;
-              if (npass == passes) { npass = 0; nt_tile = tile + gridDim.x; }
-              if (nt_tile < total_tiles) issue_residual(nt_tile, npass);
-            } else {
-              mbar_arrive(cbuf_free);
-            }
+            ++unit;
           }
         }
       }
