@@ -125,13 +125,13 @@ static int pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn)
   return best;
 }
 
-template <int BN>
+template <int BN, int EPI>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                   const CUtensorMap& r, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
@@ -139,7 +139,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   const long long tiles = static_cast<long long>((p.M + 127) / 128) * ((p.N + BN - 1) / BN) * p.Z;
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, o, r, p);
+  gemm_tc_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, o, r, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return 0;
@@ -278,7 +278,8 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
                        (g->out_z1_stride % 8) == 0 && (g->out_z2_stride % 8) == 0;
   const bool res_ok = g->residual == nullptr ||
                       ((g->ldr % 8) == 0 && (reinterpret_cast<uint64_t>(g->residual) & 15) == 0 && g->Z == 1);
-  p.epi_tma = (!g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR && aligned && res_ok) ? 1 : 0;
+  const int n_out_chk = g->geglu ? g->N / 2 : g->N;
+  p.epi_tma = (!g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR && aligned && res_ok && (n_out_chk % 8) == 0) ? 1 : 0;
   if (g->geglu && !p.epi_tma) return set_error("icd_gemm: GEGLU needs an aligned fp16 row-major output");
   if (p.epi_tma) {
     const uint64_t n_out = (uint64_t)(g->geglu ? g->N / 2 : g->N);
@@ -289,19 +290,43 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     const uint64_t s2 = g->out_z2_stride > 0 ? (uint64_t)g->out_z2_stride * 2 : s1;
     const uint64_t str[3] = {(uint64_t)g->ldc * 2, s1, s2};
     if (make_tmap_4d(&tmOut, g->out, dims, str, box, 64)) return 1;
+    p.res_tma = g->residual != nullptr ? 1 : 0;
     if (g->residual != nullptr) {
       const uint64_t rdims[4] = {n_out, (uint64_t)g->M, 1, 1};
       const uint64_t rstr[3] = {(uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2};
       if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, box, 64)) return 1;
-      p.res_tma = 1;
     }
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 64: return launch<64>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
-    case 128: return launch<128>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
-    case 160: return launch<160>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
-    default: return launch<256>(tmA0, tmA1, tmB, tmOut, tmRes, p, st);
+#define ICD_LAUNCH(BN_, EPI_) return launch<BN_, EPI_>(tmA0, tmA1, tmB, tmOut, tmRes, p, st)
+  if (g->geglu) {
+    if (bn == 128) ICD_LAUNCH(128, EPI_STAGED_GEGLU);
+    if (bn == 256) ICD_LAUNCH(256, EPI_STAGED_GEGLU);
+    return set_error("icd_gemm: GEGLU supports BN 128 / 256");
   }
+  // short main loops cannot hide the row-per-thread residual reads: stream the residual through TMA + smem
+  if (p.epi_tma && p.res_tma && p.num_kb <= 24) {
+    switch (bn) {
+      case 64: ICD_LAUNCH(64, EPI_STAGED_RES);
+      case 128: ICD_LAUNCH(128, EPI_STAGED_RES);
+      case 160: ICD_LAUNCH(160, EPI_STAGED_RES);
+      default: ICD_LAUNCH(256, EPI_STAGED_RES);
+    }
+  }
+  if (p.epi_tma) {
+    switch (bn) {
+      case 64: ICD_LAUNCH(64, EPI_STAGED);
+      case 128: ICD_LAUNCH(128, EPI_STAGED);
+      case 160: ICD_LAUNCH(160, EPI_STAGED);
+      default: ICD_LAUNCH(256, EPI_STAGED);
+    }
+  }
+  switch (bn) {
+    case 64: ICD_LAUNCH(64, EPI_DIRECT);
+    case 128: ICD_LAUNCH(128, EPI_DIRECT);
+    case 160: ICD_LAUNCH(160, EPI_DIRECT);
+    default: ICD_LAUNCH(256, EPI_DIRECT);
+  }
+#undef ICD_LAUNCH
 }

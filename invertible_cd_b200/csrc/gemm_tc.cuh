@@ -59,41 +59,45 @@ struct GemmParams {
   float alpha_t, sigma_t, alpha_s, sigma_s;
 };
 
-template <int BN>
+enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3 };
+
+template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int C_BYTES = 4 * 8192;  // epilogue staging: 4 atoms of [128 rows x 32 cols] fp16, 64B swizzle
-  static constexpr int BUDGET = 232448 - 1024 - 256 - C_BYTES;
+  static constexpr int R_BYTES = (EPI == EPI_STAGED_RES) ? 4 * 8192 : 0;  // TMA-loaded residual units (2 x 16 KB)
+  static constexpr int BUDGET = 232448 - 1024 - 256 - C_BYTES - R_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;                            // power of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + R_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int THREADS = (EPI == EPI_STAGED_RES) ? 224 : 192;  // + residual-producer warp
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GemmCfg<BN, EPI>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
   uint8_t* smem_c = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + Cfg::C_BYTES);
+  uint8_t* smem_r = smem_c + Cfg::C_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + Cfg::R_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint64_t* cbuf_free = bars + 2 * STAGES + 4;   // staging buffer reusable (previous TMA stores have read it)
-  uint64_t* res_full = bars + 2 * STAGES + 5;    // residual tile landed in the staging buffer
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  uint64_t* res_full = bars + 2 * STAGES + 4;    // [2] residual unit landed in smem_r (TMA tx-count)
+  uint64_t* res_empty = bars + 2 * STAGES + 6;   // [2] residual unit consumed by the 128 epilogue threads
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,8 +114,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 128);
     }
-    mbar_init(cbuf_free, 1);
-    mbar_init(res_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&res_full[i], 1);
+      mbar_init(&res_empty[i], 128);
+    }
     tma_prefetch_desc(&tmOut);
     tma_prefetch_desc(&tmRes);
     fence_mbar_init();
@@ -213,25 +219,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ residual producer (EPI_STAGED_RES only)
+    if constexpr (EPI == EPI_STAGED_RES) {
+      if (lane == 0) {
+        constexpr int units = (BN + 63) / 64;
+        uint32_t runit = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int z = tile / tiles_per_z;
+          const int t = tile - z * tiles_per_z;
+          const int mt = t / n_tiles, nt = t - mt * n_tiles;
+          for (int u = 0; u < units; ++u, ++runit) {
+            const int b = runit & 1;
+            mbar_wait(&res_empty[b], ((runit >> 1) & 1) ^ 1);
+            const int cols = min(64, BN - u * 64);
+            const int natoms = (cols + 31) / 32;
+            mbar_expect_tx(&res_full[b], natoms * 8192);
+            for (int a = 0; a < natoms; ++a)
+              tma_load_4d(smem_r + b * 16384 + a * 8192, &tmRes, &res_full[b], nt * BN + u * 64 + a * 32, mt * 128,
+                          0, 0);
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // NOTE: loops are deliberately rolled (#pragma unroll 1) — a fully unrolled epilogue is ~200 KB of SASS and
+    // runs out of the instruction cache (measured: 21k cycles per tile, ncu profiles/r1_c_*).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
     int iter = 0;
-    if (p.epi_tma) {
-      // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual, GEGLU) -> swizzled smem -> TMA store.
+    if constexpr (EPI != EPI_DIRECT) {
+      // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual | GEGLU) -> swizzled smem -> TMA store.
       // Output is produced in 64-column units through a double-buffered staging area (2 x [128 rows x 64 cols],
       // as 32-column atoms with 64B swizzle), so the TMA store of unit u overlaps the math of unit u+1.
-      // The residual rows are prefetched straight from global memory into registers BEFORE waiting for the
-      // accumulator, i.e. their latency hides behind the tile's main loop.
-      constexpr int OUTW = BN;                    // accumulator columns; GEGLU emits OUTW/2 output columns
-      constexpr int RES_CHUNKS = (BN + 7) / 8;    // 16-byte residual chunks per row
-      const int outw = p.geglu ? OUTW / 2 : OUTW; // output columns per tile
-      const int n_out_total = p.geglu ? p.N / 2 : p.N;
-      const int units = (outw + 63) / 64;
+      // The residual is prefetched from global memory into registers one unit ahead (the first unit of a tile
+      // BEFORE waiting for the accumulator, i.e. behind the tile's main loop).
+      constexpr bool GEGLU = (EPI == EPI_STAGED_GEGLU);
+      constexpr int outw = GEGLU ? BN / 2 : BN;   // output columns per tile
+      constexpr int units = (outw + 63) / 64;
+      const int n_out_total = GEGLU ? p.N / 2 : p.N;
       const bool leader = (warp == 2 && lane == 0);
       const uint32_t stg = smem_u32(smem_c);
       const uint32_t sw = (row_in_tile >> 1) & 3; // 64B swizzle: 16B-chunk index ^= (row / 2) % 4
+      const bool has_res = p.res_tma != 0;
       uint32_t unit = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         const int z = tile / tiles_per_z;
@@ -241,30 +272,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t acc_phase = (iter >> 1) & 1;
         const int row = mt * 128 + row_in_tile;
         const int n_out0 = nt * outw;
-        // residual prefetch (global -> registers), issued while the MMAs of this tile are still running
-        uint4 resv[RES_CHUNKS];
-        if (p.res_tma) {
-          const bool row_ok = row < p.M;
-          const __half* rp = p.residual + static_cast<long long>(row) * p.ldr + n_out0;
+        const bool row_ok = row < p.M;
+        const __half* rp = p.residual + static_cast<long long>(row) * p.ldr + n_out0;
+        uint4 rcur[8], rnxt[8];
+        auto load_res = [&](uint4* dst, int u) {
 #pragma unroll
-          for (int i = 0; i < RES_CHUNKS; ++i) {
-            resv[i] = make_uint4(0, 0, 0, 0);
-            if (row_ok && n_out0 + i * 8 < n_out_total) resv[i] = __ldg(reinterpret_cast<const uint4*>(rp + i * 8));
+          for (int i = 0; i < 8; ++i) {
+            dst[i] = make_uint4(0, 0, 0, 0);
+            const int c = u * 64 + i * 8;
+            if (has_res && row_ok && c < outw && n_out0 + c < n_out_total)
+              dst[i] = __ldg(reinterpret_cast<const uint4*>(rp + c));
           }
-        }
+        };
+        if (!GEGLU && EPI != EPI_STAGED_RES) load_res(rcur, 0);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
         const int img = min(row, p.M - 1) / p.rows_per_img;
         const float* rv = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
+#pragma unroll 1
+        for (int u = 0; u < units; ++u, ++unit) {
+          const int unit_cols = min(64, outw - u * 64);
+          const uint32_t buf = stg + (unit & 1) * 16384;
+          if (!GEGLU && EPI != EPI_STAGED_RES && u + 1 < units) load_res(rnxt, u + 1);
+          if constexpr (EPI == EPI_STAGED_RES) mbar_wait(&res_full[unit & 1], (unit >> 1) & 1);
+          // staging buffer (unit & 1) was last used by unit-2: its TMA store must have finished reading smem
+          if (leader) bulk_wait_read1();
+          named_bar_sync(1, 128);
+          if constexpr (GEGLU) {
+#pragma unroll 1
+            for (int c16 = 0; c16 < unit_cols; c16 += 16) {
+              const int col_t = u * 64 + c16;
+              float hv[16], gv[16];
+              tmem_ld16(t_addr + col_t, hv);
+              tmem_ld16(t_addr + BN / 2 + col_t, gv);
+              tmem_ld_wait();
+              const float4* bh = reinterpret_cast<const float4*>(p.bias + nt * BN + col_t);
+              const float4* bg = reinterpret_cast<const float4*>(p.bias + nt * BN + BN / 2 + col_t);
+              uint32_t o[8];
 #pragma unroll
-        for (int u = 0; u < (OUTW + 63) / 64; ++u) {
-          if (u < units) {
-            const int unit_cols = min(64, outw - u * 64);
-            const uint32_t buf = stg + (unit & 1) * 16384;
-            // staging buffer (unit & 1) was last used by unit-2: its TMA store must have finished reading smem
-            if (leader) bulk_wait_read1();
-            named_bar_sync(1, 128);
+              for (int j4 = 0; j4 < 4; ++j4) {
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (p.bias != nullptr) { b0 = __ldg(bh + j4); b1 = __ldg(bg + j4); }
+                const float r0 = (hv[j4 * 4 + 0] * p.alpha + b0.x) * gelu_erf(gv[j4 * 4 + 0] * p.alpha + b1.x);
+                const float r1 = (hv[j4 * 4 + 1] * p.alpha + b0.y) * gelu_erf(gv[j4 * 4 + 1] * p.alpha + b1.y);
+                const float r2 = (hv[j4 * 4 + 2] * p.alpha + b0.z) * gelu_erf(gv[j4 * 4 + 2] * p.alpha + b1.z);
+                const float r3 = (hv[j4 * 4 + 3] * p.alpha + b0.w) * gelu_erf(gv[j4 * 4 + 3] * p.alpha + b1.w);
+                const __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
+                o[j4 * 2] = *reinterpret_cast<const uint32_t*>(&h01);
+                o[j4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+              }
+              const uint32_t atom = buf + (c16 >> 5) * 8192 + row_in_tile * 64;
+              const uint32_t ch = (c16 & 16) >> 3;   // first 16B chunk (0 or 2) of this 16-column group
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + (((ch) ^ sw) << 4)), "r"(o[0]),
+                           "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + (((ch + 1) ^ sw) << 4)), "r"(o[4]),
+                           "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            }
+          } else {
 #pragma unroll
             for (int h32 = 0; h32 < 2; ++h32) {
               const int c0 = h32 * 32;
@@ -272,71 +337,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const int ncol = n_out0 + col_t;       // global output column
               if (c0 < unit_cols && ncol < n_out_total) {   // warp-uniform
                 float v[32];
-                if (p.geglu) {
-                  float gt[32];
-                  tmem_ld32(t_addr + col_t, v);
-                  tmem_ld32(t_addr + OUTW / 2 + col_t, gt);
-                  tmem_ld_wait();
-                  const float4* bh = reinterpret_cast<const float4*>(p.bias + nt * BN + col_t);
-                  const float4* bg = reinterpret_cast<const float4*>(p.bias + nt * BN + OUTW / 2 + col_t);
+                tmem_ld32(t_addr + col_t, v);
+                tmem_ld_wait();
 #pragma unroll
-                  for (int j4 = 0; j4 < 8; ++j4) {
-                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                    if (p.bias != nullptr) { b0 = __ldg(bh + j4); b1 = __ldg(bg + j4); }
-                    const float hb[4] = {b0.x, b0.y, b0.z, b0.w}, gb[4] = {b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                      const int j = j4 * 4 + q;
-                      v[j] = (v[j] * p.alpha + hb[q]) * gelu_erf(gt[j] * p.alpha + gb[q]);
-                    }
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                  if (ncol + j4 * 4 < n_out_total) {   // N_out % 8 == 0 in staged mode: whole groups
+                    if (p.bias != nullptr) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + j4);
+                    if (rv != nullptr) b1 = __ldg(reinterpret_cast<const float4*>(rv + ncol) + j4);
                   }
-                } else {
-                  tmem_ld32(t_addr + col_t, v);
-                  tmem_ld_wait();
-                  if (ncol + 32 <= n_out_total && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias + ncol) & 15) == 0) &&
-                      (rv == nullptr || (reinterpret_cast<uintptr_t>(rv + ncol) & 15) == 0)) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                      if (p.bias != nullptr) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + j4);
-                      if (rv != nullptr) b1 = __ldg(reinterpret_cast<const float4*>(rv + ncol) + j4);
-                      v[j4 * 4 + 0] = v[j4 * 4 + 0] * p.alpha + (b0.x + b1.x);
-                      v[j4 * 4 + 1] = v[j4 * 4 + 1] * p.alpha + (b0.y + b1.y);
-                      v[j4 * 4 + 2] = v[j4 * 4 + 2] * p.alpha + (b0.z + b1.z);
-                      v[j4 * 4 + 3] = v[j4 * 4 + 3] * p.alpha + (b0.w + b1.w);
-                    }
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                      float x = v[j] * p.alpha;
-                      if (ncol + j < n_out_total) {
-                        if (p.bias != nullptr) x += __ldg(p.bias + ncol + j);
-                        if (rv != nullptr) x += __ldg(rv + ncol + j);
-                      }
-                      v[j] = x;
-                    }
-                  }
+                  v[j4 * 4 + 0] = v[j4 * 4 + 0] * p.alpha + (b0.x + b1.x);
+                  v[j4 * 4 + 1] = v[j4 * 4 + 1] * p.alpha + (b0.y + b1.y);
+                  v[j4 * 4 + 2] = v[j4 * 4 + 2] * p.alpha + (b0.z + b1.z);
+                  v[j4 * 4 + 3] = v[j4 * 4 + 3] * p.alpha + (b0.w + b1.w);
                 }
                 const uint32_t atom = buf + h32 * 8192 + row_in_tile * 64;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
-                  if (p.res_tma) {
-                    const int ci = (col_t >> 3) + cc;
-                    if (ci < RES_CHUNKS) {
-                      const uint4 rr = resv[ci];
-                      const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                      for (int q = 0; q < 4; ++q) {
-                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[q]));
-                        v[cc * 8 + 2 * q] += f.x;
-                        v[cc * 8 + 2 * q + 1] += f.y;
-                      }
-                    }
+                  uint4 rr;
+                  if constexpr (EPI == EPI_STAGED_RES) {
+                    const uint32_t ra = smem_u32(smem_r) + (unit & 1) * 16384 + h32 * 8192 + row_in_tile * 64 +
+                                        ((cc ^ sw) << 4);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w)
+                                 : "r"(ra));
+                  } else {
+                    rr = rcur[h32 * 4 + cc];
                   }
+                  const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
                   uint32_t o[4];
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
-                    const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q], v[cc * 8 + 2 * q + 1]);
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[q]));
+                    const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q] + f.x, v[cc * 8 + 2 * q + 1] + f.y);
                     o[q] = *reinterpret_cast<const uint32_t*>(&h2);
                   }
                   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + ((cc ^ sw) << 4)), "r"(o[0]),
@@ -345,146 +378,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
               }
             }
-            if (u == units - 1) {   // all TMEM reads of this accumulator are done
-              tc_fence_before();
-              mbar_arrive(&tmem_empty[acc]);
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(2, 128);
-            if (leader) {
+            if constexpr (EPI == EPI_STAGED_RES) {
+              mbar_arrive(&res_empty[unit & 1]);
+            } else {
 #pragma unroll
-              for (int h32 = 0; h32 < 2; ++h32) {
-                const int ncol = n_out0 + u * 64 + h32 * 32;
-                if (h32 * 32 < unit_cols && ncol < n_out_total)
-                  tma_store_4d(&tmOut, smem_c + (unit & 1) * 16384 + h32 * 8192, ncol, mt * 128, z % p.ZA1,
-                               z / p.ZA1);
-              }
-              bulk_commit();
+              for (int i = 0; i < 8; ++i) rcur[i] = rnxt[i];
             }
-            ++unit;
+          }
+          if (u == units - 1) {   // all TMEM reads of this accumulator are done
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (leader) {
+#pragma unroll
+            for (int h32 = 0; h32 < 2; ++h32) {
+              const int ncol = n_out0 + u * 64 + h32 * 32;
+              if (h32 * 32 < unit_cols && ncol < n_out_total)
+                tma_store_4d(&tmOut, smem_c + (unit & 1) * 16384 + h32 * 8192, ncol, mt * 128, z % p.ZA1,
+                             z / p.ZA1);
+            }
+            bulk_commit();
           }
         }
       }
       if (leader) bulk_wait0();
-    } else
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const int z = tile / tiles_per_z;
-      const int t = tile - z * tiles_per_z;
-      const int mt = t / n_tiles, nt = t - mt * n_tiles;
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const long long out_zoff = (z % p.ZA1) * p.out_z1_stride + (z / p.ZA1) * p.out_z2_stride;
-      const uint32_t t_addr = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
-      const int row = mt * 128 + row_in_tile;
-      const bool row_ok = row < p.M;
-      const int img = row / p.rows_per_img;
-      const int row_in_img = row - img * p.rows_per_img;
-      const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
-      const __half* res = (p.residual != nullptr && row_ok)
-                              ? p.residual + z * p.res_zstride + static_cast<long long>(row) * p.ldr
-                              : nullptr;
-
-      constexpr int OUT_COLS = BN;  // accumulator columns of this tile
-      if (p.geglu) {
-        // columns [0, BN/2) = h, [BN/2, BN) = gate; output column = nt*BN/2 + j
-        const int n_out0 = nt * (BN / 2);
-        const int n_out_total = p.N / 2;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += 16) {
-          float h[16], g[16];
-          tmem_ld16(t_addr + c0, h);
-          tmem_ld16(t_addr + BN / 2 + c0, g);
-          tmem_ld_wait();
-          if (row_ok) {
-            __half o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int nb = nt * BN + c0 + j;  // index into (permuted) bias
-              float hv = h[j] * p.alpha, gv = g[j] * p.alpha;
-              if (p.bias != nullptr && n_out0 + c0 + j < n_out_total) {
-                hv += p.bias[nb];
-                gv += p.bias[nb + BN / 2];
-              }
-              o[j] = __float2half_rn(hv * gelu_erf(gv));
-            }
-            __half* op = reinterpret_cast<__half*>(p.out) + out_zoff + static_cast<long long>(row) * p.ldc +
-                         n_out0 + c0;
-            if (n_out0 + c0 + 16 <= n_out_total && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-              reinterpret_cast<uint4*>(op)[0] = reinterpret_cast<uint4*>(o)[0];
-              reinterpret_cast<uint4*>(op)[1] = reinterpret_cast<uint4*>(o)[1];
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (n_out0 + c0 + j < n_out_total) op[j] = o[j];
-            }
-          }
-        }
-      } else {
+    } else {
+      // ---- direct epilogue (fp32 / transposed / unaligned outputs: conv_out, time-embedding GEMMs, N tails)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int z = tile / tiles_per_z;
+        const int t = tile - z * tiles_per_z;
+        const int mt = t / n_tiles, nt = t - mt * n_tiles;
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const long long out_zoff = (z % p.ZA1) * p.out_z1_stride + (z / p.ZA1) * p.out_z2_stride;
+        const uint32_t t_addr = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
+        const int row = mt * 128 + row_in_tile;
+        const bool row_ok = row < p.M;
+        const int img = row / p.rows_per_img;
+        const int row_in_img = row - img * p.rows_per_img;
+        const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
+        const __half* res = (p.residual != nullptr && row_ok)
+                                ? p.residual + z * p.res_zstride + static_cast<long long>(row) * p.ldr
+                                : nullptr;
         const int n0 = nt * BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < OUT_COLS; c0 += 16) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
           if (n0 + c0 >= p.N) break;  // warp-uniform
           float v[16];
           tmem_ld16(t_addr + c0, v);
           tmem_ld_wait();
           if (row_ok) {
             const int nbase = n0 + c0;
-            const bool full = nbase + 16 <= p.N;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float x = v[j] * p.alpha;
-              if (full || nbase + j < p.N) {
+              if (nbase + j < p.N) {
                 if (p.bias != nullptr) x += p.bias[nbase + j];
                 if (rv != nullptr) x += rv[nbase + j];
+                if (res != nullptr) x += __half2float(res[nbase + j]);
               }
               v[j] = x;
             }
-            if (res != nullptr) {
-              if (full && ((reinterpret_cast<uintptr_t>(res + nbase) & 15) == 0)) {
-                uint4 r0 = reinterpret_cast<const uint4*>(res + nbase)[0];
-                uint4 r1 = reinterpret_cast<const uint4*>(res + nbase)[1];
-                const __half* rh0 = reinterpret_cast<const __half*>(&r0);
-                const __half* rh1 = reinterpret_cast<const __half*>(&r1);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  v[j] += __half2float(rh0[j]);
-                  v[8 + j] += __half2float(rh1[j]);
-                }
-              } else {
-                for (int j = 0; j < 16; ++j)
-                  if (nbase + j < p.N) v[j] += __half2float(res[nbase + j]);
-              }
-            }
             if (p.out_mode == GEMM_OUT_ROWMAJOR) {
-              if (p.out_fp32) {
-                float* op = reinterpret_cast<float*>(p.out) + out_zoff + static_cast<long long>(row) * p.ldc +
-                            nbase;
-                if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+              const long long o0 = out_zoff + static_cast<long long>(row) * p.ldc + nbase;
 #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                  for (int j = 0; j < 16; ++j)
-                    if (nbase + j < p.N) op[j] = v[j];
-                }
-              } else {
-                __half o[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = __float2half_rn(v[j]);
-                __half* op = reinterpret_cast<__half*>(p.out) + out_zoff +
-                             static_cast<long long>(row) * p.ldc + nbase;
-                if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-                  reinterpret_cast<uint4*>(op)[0] = reinterpret_cast<uint4*>(o)[0];
-                  reinterpret_cast<uint4*>(op)[1] = reinterpret_cast<uint4*>(o)[1];
-                } else {
-                  for (int j = 0; j < 16; ++j)
-                    if (nbase + j < p.N) op[j] = o[j];
+              for (int j = 0; j < 16; ++j) {
+                if (nbase + j < p.N) {
+                  if (p.out_fp32) reinterpret_cast<float*>(p.out)[o0 + j] = v[j];
+                  else reinterpret_cast<__half*>(p.out)[o0 + j] = __float2half_rn(v[j]);
                 }
               }
             } else {
               // transposed: element (row, n) -> out[z][img][n][row_in_img]; consecutive lanes = consecutive rows
               const long long base = out_zoff + static_cast<long long>(img) * p.out_imgstride + row_in_img;
+#pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (nbase + j < p.N) {
                   const long long idx = base + static_cast<long long>(nbase + j) * p.ldc;
@@ -503,9 +474,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
     }
   }
 
