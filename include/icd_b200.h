@@ -68,6 +68,7 @@ typedef struct IcdGemm {
   int out_mode;            /* 0 row-major [M][ldc]; 1 transposed out[img][n][row_in_img] with column stride ldc */
   int geglu;               /* B rows packed per BN tile as [h | gate]; out[:, j] = h_j * gelu(g_j); N counts packed rows */
   int force_bn;            /* 0 = heuristic, else 64/128/160/256 */
+  int force_bm;            /* 0 = heuristic, else 128/256 (rows per CTA tile) */
   /* fused consistency update on the (transposed, fp32) output — utils/generation.py:136-155 */
   const float* upd_x;
   float* upd_out;

@@ -101,45 +101,62 @@ int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], cons
   return 0;
 }
 
-static int pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn) {
-  if (force_bn != 0) return force_bn;
+// Tile-shape heuristic. Every operand byte is fetched from L2 by each CTA that needs it, and a 128x160 tile at
+// full tensor rate would need ~31 TB/s of L2->SM traffic (measured cap ~12 TB/s, profiles/r1_c_*), so the model
+// charges each K block max(MMA time, L2 time) and prefers 256-row tiles (two MMA halves share one B tile).
+struct TileChoice { int bm, bn; };
+static TileChoice pick_tile(int M, int N, int Z, int num_kb, int geglu, int b_mn_major, int force_bn, int force_bm) {
   const int sms = sm_count();
-  const long long m_tiles = (M + 127) / 128;
-  const int cands_k[4] = {256, 160, 128, 64};
-  int best = 128;
+  const int bns[4] = {256, 160, 128, 64};
+  const int bms[2] = {128, 256};
+  TileChoice best{128, 128};
   double best_cost = 1e30;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands_k[i];
-    if ((b_mn_major || geglu) && bn == 160) continue;
-    if (geglu && (N % bn) != 0) continue;
-    if (bn > 64 && N <= bn / 2) continue;  // mostly-empty tile
-    const long long tiles = m_tiles * ((N + bn - 1) / bn) * Z;
-    const long long waves = (tiles + sms - 1) / sms;
-    // per-tile time ~ MMA time (prop. to BN) + fixed epilogue/pipeline overhead
-    const double cost = static_cast<double>(waves) * (bn + 24);
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+  for (int bi = 0; bi < 2; ++bi) {
+    const int bm = bms[bi];
+    if (force_bm != 0 && bm != force_bm) continue;
+    if (force_bm == 0 && bm == 256 && (geglu || b_mn_major || M <= 128)) continue;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = bns[i];
+      if (force_bn != 0 && bn != force_bn) continue;
+      if (force_bn == 0) {
+        if ((b_mn_major || geglu) && bn == 160) continue;
+        if (geglu && ((N % bn) != 0 || bn < 128)) continue;
+        if (bn > 64 && N <= bn / 2) continue;  // mostly-empty tile
+      }
+      const long long tiles = static_cast<long long>((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Z;
+      const long long waves = (tiles + sms - 1) / sms;
+      const double mma = bm * bn / 64.0;               // cycles per 64-deep K block
+      const double l2 = 3.0 * (bm + bn);               // (bm+bn) * 128 B / ~42.5 B/clk/SM
+      const double mainloop = num_kb * (mma > l2 ? mma : l2) + 1500.0;
+      const double epi = (bm / 128) * (600.0 + 6.0 * bn) * (geglu ? 3.0 : 1.0);
+      const int half_stride = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
+      const bool dbl = 2 * (bm / 128) * half_stride <= 512;
+      const double per_tile = dbl ? (mainloop > epi ? mainloop : epi) : mainloop + epi;
+      const double cost = waves * per_tile + (dbl ? epi : 0.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = TileChoice{bm, bn};
+      }
     }
   }
   return best;
 }
 
-template <int BN, int EPI>
+template <int BM, int BN, int EPI>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                   const CUtensorMap& r, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, EPI>;
+  using Cfg = GemmCfg<BM, BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BM, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  const long long tiles = static_cast<long long>((p.M + 127) / 128) * ((p.N + BN - 1) / BN) * p.Z;
+  const long long tiles = static_cast<long long>((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.Z;
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, o, r, p);
+  gemm_tc_kernel<BM, BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, o, r, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return 0;
@@ -150,14 +167,18 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
 using namespace icd;
 
 extern "C" int icd_gemm_pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn) {
-  return pick_bn(M, N, Z, geglu, b_mn_major, force_bn);
+  return pick_tile(M, N, Z, 16, geglu, b_mn_major, force_bn, 0).bn;
 }
 
 extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   if (g == nullptr || g->a0 == nullptr || g->b == nullptr || g->out == nullptr)
     return set_error("icd_gemm: null operand");
   if (g->M <= 0 || g->N <= 0 || g->Z <= 0) return set_error("icd_gemm: empty problem");
-  const int bn = pick_bn(g->M, g->N, g->Z, g->geglu, g->b_mn_major, g->force_bn);
+  const int kb_est = ((g->K0 + 63) / 64 + (g->a1 != nullptr ? (g->K1 + 63) / 64 : 0)) * (g->a_mode == 1 ? 9 : 1);
+  // small-K GEMMs with a residual use the TMA-streamed residual variant, which exists for 128-row tiles only
+  const int fbm = (g->force_bm == 0 && g->residual != nullptr && kb_est <= 24) ? 128 : g->force_bm;
+  const TileChoice tc = pick_tile(g->M, g->N, g->Z, kb_est, g->geglu, g->b_mn_major, g->force_bn, fbm);
+  const int bn = tc.bn, bm = tc.bm;
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error("icd_gemm: unsupported BN");
   if (g->b_mn_major && (bn % 64) != 0) return set_error("icd_gemm: MN-major B needs BN multiple of 64");
   if (g->geglu && (g->N % bn) != 0) return set_error("icd_gemm: GEGLU needs N % BN == 0");
@@ -299,34 +320,28 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define ICD_LAUNCH(BN_, EPI_) return launch<BN_, EPI_>(tmA0, tmA1, tmB, tmOut, tmRes, p, st)
+#define ICD_LAUNCH(BM_, BN_, EPI_) return launch<BM_, BN_, EPI_>(tmA0, tmA1, tmB, tmOut, tmRes, p, st)
+#define ICD_LAUNCH_BN(BM_, EPI_)                 \
+  switch (bn) {                                  \
+    case 64: ICD_LAUNCH(BM_, 64, EPI_);          \
+    case 128: ICD_LAUNCH(BM_, 128, EPI_);        \
+    case 160: ICD_LAUNCH(BM_, 160, EPI_);        \
+    default: ICD_LAUNCH(BM_, 256, EPI_);         \
+  }
   if (g->geglu) {
-    if (bn == 128) ICD_LAUNCH(128, EPI_STAGED_GEGLU);
-    if (bn == 256) ICD_LAUNCH(256, EPI_STAGED_GEGLU);
+    if (bm != 128) return set_error("icd_gemm: GEGLU uses 128-row tiles");
+    if (bn == 128) ICD_LAUNCH(128, 128, EPI_STAGED_GEGLU);
+    if (bn == 256) ICD_LAUNCH(128, 256, EPI_STAGED_GEGLU);
     return set_error("icd_gemm: GEGLU supports BN 128 / 256");
   }
   // short main loops cannot hide the row-per-thread residual reads: stream the residual through TMA + smem
-  if (p.epi_tma && p.res_tma && p.num_kb <= 24) {
-    switch (bn) {
-      case 64: ICD_LAUNCH(64, EPI_STAGED_RES);
-      case 128: ICD_LAUNCH(128, EPI_STAGED_RES);
-      case 160: ICD_LAUNCH(160, EPI_STAGED_RES);
-      default: ICD_LAUNCH(256, EPI_STAGED_RES);
-    }
-  }
+  if (p.epi_tma && p.res_tma && p.num_kb <= 24 && bm == 128) { ICD_LAUNCH_BN(128, EPI_STAGED_RES) }
   if (p.epi_tma) {
-    switch (bn) {
-      case 64: ICD_LAUNCH(64, EPI_STAGED);
-      case 128: ICD_LAUNCH(128, EPI_STAGED);
-      case 160: ICD_LAUNCH(160, EPI_STAGED);
-      default: ICD_LAUNCH(256, EPI_STAGED);
-    }
+    if (bm == 256) { ICD_LAUNCH_BN(256, EPI_STAGED) }
+    ICD_LAUNCH_BN(128, EPI_STAGED)
   }
-  switch (bn) {
-    case 64: ICD_LAUNCH(64, EPI_DIRECT);
-    case 128: ICD_LAUNCH(128, EPI_DIRECT);
-    case 160: ICD_LAUNCH(160, EPI_DIRECT);
-    default: ICD_LAUNCH(256, EPI_DIRECT);
-  }
+  if (bm == 256) { ICD_LAUNCH_BN(256, EPI_DIRECT) }
+  ICD_LAUNCH_BN(128, EPI_DIRECT)
+#undef ICD_LAUNCH_BN
 #undef ICD_LAUNCH
 }

@@ -61,9 +61,10 @@ struct GemmParams {
 
 enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3 };
 
-template <int BN, int EPI>
+template <int BM_, int BN, int EPI>
 struct GemmCfg {
-  static constexpr int BM = 128, BK = 64;
+  static constexpr int BM = BM_, BK = 64;
+  static constexpr int HALVES = BM / 128;            // 128-row MMA halves per tile (1 or 2)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -71,18 +72,21 @@ struct GemmCfg {
   static constexpr int R_BYTES = (EPI == EPI_STAGED_RES) ? 4 * 8192 : 0;  // TMA-loaded residual units (2 x 16 KB)
   static constexpr int BUDGET = 232448 - 1024 - 256 - C_BYTES - R_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;                            // power of two >= 32
+  static constexpr int HALF_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per 128-row half
+  static constexpr int ACC_COLS = HALVES * HALF_STRIDE;                        // one accumulator set
+  static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;             // double-buffer when TMEM allows
+  static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;                      // power of two in [64, 512]
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + R_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = (EPI == EPI_STAGED_RES) ? 224 : 192;  // + residual-producer warp
 };
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN, EPI>::THREADS, 1)
+template <int BM, int BN, int EPI>
+__global__ void __launch_bounds__(GemmCfg<BM, BN, EPI>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
-  using Cfg = GemmCfg<BN, EPI>;
+  using Cfg = GemmCfg<BM, BN, EPI>;
+  constexpr int HALVES = Cfg::HALVES, ACC_STAGES = Cfg::ACC_STAGES;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int m_tiles = (p.M + 127) / 128;
+  const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles_per_z = m_tiles * n_tiles;
   const int total_tiles = tiles_per_z * p.Z;
@@ -143,18 +147,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int z = tile / tiles_per_z;
         const int t = tile - z * tiles_per_z;
         const int mt = t / n_tiles, nt = t - mt * n_tiles;
-        const int m0 = mt * 128, n0 = nt * BN;
-        // conv tile origin
-        int cb = 0, cy = 0, cx = 0;
-        if (p.a_mode == GEMM_A_CONV3X3) {
-          const int hw = p.H * p.W;
-          if (p.tile_b > 1) {
-            cb = mt * p.tile_b;
-          } else {
-            cb = m0 / hw;
-            const int rem = m0 - cb * hw;
-            cy = rem / p.W;
-            cx = rem - cy * p.W;
+        const int n0 = nt * BN;
+        // origin of each 128-row half (conv: image / row / column of its first pixel)
+        int m0h[HALVES], cb[HALVES], cy[HALVES], cx[HALVES];
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          const int st = mt * HALVES + h;   // 128-row sub-tile index
+          m0h[h] = st * 128;
+          cb[h] = cy[h] = cx[h] = 0;
+          if (p.a_mode == GEMM_A_CONV3X3) {
+            const int hw = p.H * p.W;
+            if (p.tile_b > 1) {
+              cb[h] = st * p.tile_b;
+            } else {
+              cb[h] = m0h[h] / hw;
+              const int rem = m0h[h] - cb[h] * hw;
+              cy[h] = rem / p.W;
+              cx[h] = rem - cy[h] * p.W;
+            }
           }
         }
         const int bz1 = p.b_batched ? z % p.ZB1 : 0, bz2 = p.b_batched ? z / p.ZB1 : 0;
@@ -165,13 +175,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int r = kb - tap * p.kb_per_tap;
           const CUtensorMap* ma = (r < p.kb_split) ? &tmA0 : &tmA1;
           const int ka = (r < p.kb_split ? r : r - p.kb_split) * 64;
-          void* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           void* sb = smem_b + stage * Cfg::B_BYTES;
-          if (p.a_mode == GEMM_A_CONV3X3) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, ma, &full_bar[stage], ka, cx + kx - 1, cy + ky - 1, cb);
-          } else {
-            tma_load_4d(sa, ma, &full_bar[stage], ka, m0, z % p.ZA1, z / p.ZA1);
+#pragma unroll
+          for (int h = 0; h < HALVES; ++h) {
+            if (p.a_mode == GEMM_A_CONV3X3) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d(sa + h * 16384, ma, &full_bar[stage], ka, cx[h] + kx - 1, cy[h] + ky - 1, cb[h]);
+            } else {
+              tma_load_4d(sa + h * 16384, ma, &full_bar[stage], ka, m0h[h], z % p.ZA1, z / p.ZA1);
+            }
           }
           if (p.b_mn_major) {
             // B tile = BN/64 boxes of [64 K rows][64 N], one per 64-wide N atom
@@ -196,11 +209,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t phase = 0;
       int iter = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
+        const int acc = iter % ACC_STAGES;
+        const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -208,10 +221,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t db = p.b_mn_major ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
                                              : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+#pragma unroll
+            for (int h = 0; h < HALVES; ++h) {
+              const uint64_t da = umma_smem_desc(a_addr + h * 16384 + k * 32, 16, 1024);
+              umma_f16_ss(d_tmem + h * Cfg::HALF_STRIDE, da, db, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -229,15 +245,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int z = tile / tiles_per_z;
           const int t = tile - z * tiles_per_z;
           const int mt = t / n_tiles, nt = t - mt * n_tiles;
-          for (int u = 0; u < units; ++u, ++runit) {
-            const int b = runit & 1;
-            mbar_wait(&res_empty[b], ((runit >> 1) & 1) ^ 1);
-            const int cols = min(64, BN - u * 64);
-            const int natoms = (cols + 31) / 32;
-            mbar_expect_tx(&res_full[b], natoms * 8192);
-            for (int a = 0; a < natoms; ++a)
-              tma_load_4d(smem_r + b * 16384 + a * 8192, &tmRes, &res_full[b], nt * BN + u * 64 + a * 32, mt * 128,
-                          0, 0);
+          for (int half = 0; half < HALVES; ++half) {
+            for (int u = 0; u < units; ++u, ++runit) {
+              const int b = runit & 1;
+              mbar_wait(&res_empty[b], ((runit >> 1) & 1) ^ 1);
+              const int cols = min(64, BN - u * 64);
+              const int natoms = (cols + 31) / 32;
+              mbar_expect_tx(&res_full[b], natoms * 8192);
+              for (int a = 0; a < natoms; ++a)
+                tma_load_4d(smem_r + b * 16384 + a * 8192, &tmRes, &res_full[b], nt * BN + u * 64 + a * 32,
+                            mt * BM + half * 128, 0, 0);
+            }
           }
         }
       }
@@ -268,10 +286,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int z = tile / tiles_per_z;
         const int t = tile - z * tiles_per_z;
         const int mt = t / n_tiles, nt = t - mt * n_tiles;
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
-        const int row = mt * 128 + row_in_tile;
+        const int acc = iter % ACC_STAGES;
+        const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
         const int n_out0 = nt * outw;
+#pragma unroll 1
+        for (int half = 0; half < HALVES; ++half) {
+        const int row = mt * BM + half * 128 + row_in_tile;
         const bool row_ok = row < p.M;
         const __half* rp = p.residual + static_cast<long long>(row) * p.ldr + n_out0;
         uint4 rcur[8], rnxt[8];
@@ -285,9 +305,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         };
         if (!GEGLU && EPI != EPI_STAGED_RES) load_res(rcur, 0);
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
+        if (half == 0) {
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+        }
+        const uint32_t t_addr = tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE +
+                                (static_cast<uint32_t>(quad * 32) << 16);
         const int img = min(row, p.M - 1) / p.rows_per_img;
         const float* rv = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
 #pragma unroll 1
@@ -385,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int i = 0; i < 8; ++i) rcur[i] = rnxt[i];
             }
           }
-          if (u == units - 1) {   // all TMEM reads of this accumulator are done
+          if (u == units - 1 && half == HALVES - 1) {   // all TMEM reads of this accumulator are done
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
           }
@@ -396,12 +419,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int h32 = 0; h32 < 2; ++h32) {
               const int ncol = n_out0 + u * 64 + h32 * 32;
               if (h32 * 32 < unit_cols && ncol < n_out_total)
-                tma_store_4d(&tmOut, smem_c + (unit & 1) * 16384 + h32 * 8192, ncol, mt * 128, z % p.ZA1,
-                             z / p.ZA1);
+                tma_store_4d(&tmOut, smem_c + (unit & 1) * 16384 + h32 * 8192, ncol, mt * BM + half * 128,
+                             z % p.ZA1, z / p.ZA1);
             }
             bulk_commit();
           }
         }
+        }  // half
       }
       if (leader) bulk_wait0();
     } else {
@@ -410,13 +434,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int z = tile / tiles_per_z;
         const int t = tile - z * tiles_per_z;
         const int mt = t / n_tiles, nt = t - mt * n_tiles;
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
+        const int acc = iter % ACC_STAGES;
+        const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const long long out_zoff = (z % p.ZA1) * p.out_z1_stride + (z / p.ZA1) * p.out_z2_stride;
-        const uint32_t t_addr = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
-        const int row = mt * 128 + row_in_tile;
+#pragma unroll 1
+        for (int half = 0; half < HALVES; ++half) {
+        const uint32_t t_addr = tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE +
+                                (static_cast<uint32_t>(quad * 32) << 16);
+        const int row = mt * BM + half * 128 + row_in_tile;
         const bool row_ok = row < p.M;
         const int img = row / p.rows_per_img;
         const int row_in_img = row - img * p.rows_per_img;
@@ -474,6 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
+        }  // half
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       }

@@ -75,7 +75,7 @@ def pick_bn(M, N, Z=1, geglu=False, b_mn_major=False, force_bn=0):
 
 
 def linear(a, w, bias=None, out=None, residual=None, a1=None, rowvec=None, rows_per_img=0, geglu=False,
-           out_fp32=False, alpha=1.0, force_bn=0):
+           out_fp32=False, alpha=1.0, force_bn=0, force_bm=0):
     """out[M, N] = epilogue(alpha * [a | a1] @ w.T).  a: [M, K0] (row stride allowed), w: [N, K0+K1]."""
     _f16(a, "a"); _f16(w, "w")
     M, K0 = a.shape
@@ -88,12 +88,13 @@ def linear(a, w, bias=None, out=None, residual=None, a1=None, rowvec=None, rows_
              ZA1=1, b=w, b_ld=w.stride(0), ZB1=1, M=M, N=N, K=K0 + K1, Z=1, alpha=alpha, bias=bias, rowvec=rowvec,
              rows_per_img=rows_per_img, ldv=rowvec.stride(0) if rowvec is not None else 0, residual=residual,
              ldr=residual.stride(0) if residual is not None else 0, out=out, ldc=out.stride(0),
-             out_fp32=int(out.dtype == torch.float32), out_mode=0, geglu=int(geglu), force_bn=force_bn)
+             out_fp32=int(out.dtype == torch.float32), out_mode=0, geglu=int(geglu), force_bn=force_bn,
+             force_bm=force_bm)
     return out
 
 
 def conv3x3(x0, w, B, H, W, bias=None, x1=None, rowvec=None, residual=None, out=None, out_fp32=False,
-            nchw_out=None, upd_x=None, upd_out=None, upd_coefs=None, force_bn=0):
+            nchw_out=None, upd_x=None, upd_out=None, upd_coefs=None, force_bn=0, force_bm=0):
     """3x3 / pad 1 / stride 1 convolution as implicit GEMM.
     x0: [B*H*W, C0] (NHWC), optional x1: [B*H*W, C1] concatenated along channels; w: [Cout, 9*(C0+C1)] packed
     (ky, kx, cin). `nchw_out`: fp32 [B, Cout, H, W] transposed store (conv_out); with upd_* the consistency
@@ -106,7 +107,8 @@ def conv3x3(x0, w, B, H, W, bias=None, x1=None, rowvec=None, residual=None, out=
     kw = dict(a0=x0, a1=x1, a_mode=1, K0=C0, K1=C1, a0_ld=x0.stride(0), a1_ld=x1.stride(0) if x1 is not None else 0,
               B=B, H=H, W=W, b=w, b_ld=w.stride(0), ZB1=1, M=M, N=N, K=C0 + C1, Z=1, alpha=1.0, bias=bias,
               rowvec=rowvec, rows_per_img=H * W, ldv=rowvec.stride(0) if rowvec is not None else 0,
-              residual=residual, ldr=residual.stride(0) if residual is not None else 0, force_bn=force_bn)
+              residual=residual, ldr=residual.stride(0) if residual is not None else 0, force_bn=force_bn,
+              force_bm=force_bm)
     if nchw_out is not None:
         kw.update(out=nchw_out, ldc=H * W, out_imgstride=N * H * W, out_fp32=1, out_mode=1)
         if upd_x is not None:

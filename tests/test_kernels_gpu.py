@@ -44,6 +44,19 @@ def test_linear_bias_residual(ops, M, K, N, bn):
     _close(out, ref, what=f"linear {M}x{K}x{N} bn={bn}")
 
 
+@pytest.mark.parametrize("M,K,N,bn", [(1000, 1280, 640, 128), (4096, 640, 1280, 256), (700, 320, 320, 160),
+                                      (8192, 2560, 640, 0), (300, 192, 64, 64)])
+def test_linear_256row_tiles(ops, M, K, N, bn):
+    """BM=256 variant: two 128-row MMA halves share each B tile (halves the L2->SM operand traffic)."""
+    a, w = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    res = _rand(M, N, seed=3)
+    out = ops.linear(a, w, bias=bias, residual=res, force_bn=bn, force_bm=256)
+    _close(out, a.float() @ w.float().t() + bias + res.float(), what=f"linear bm256 {M}x{K}x{N} bn={bn}")
+    out32 = ops.linear(a, w, bias=bias, out_fp32=True, force_bn=bn, force_bm=256)     # direct epilogue
+    _close(out32, a.float() @ w.float().t() + bias, rtol=1e-4, atol=1e-3, what="bm256 fp32")
+
+
 def test_linear_fp32_out_and_alpha(ops):
     a, w = _rand(200, 192, seed=4), _rand(96, 192, scale=0.1, seed=5)
     out = ops.linear(a, w, out_fp32=True, alpha=0.25)
@@ -109,6 +122,18 @@ def test_conv3x3(ops, B, H, W, Cin, Cout):
     bias = torch.randn(Cout, device="cuda")
     out = ops.conv3x3(x, pack_conv3x3(w), B, H, W, bias=bias)
     _close(out, _conv_ref(x, w, B, H, W, bias), what=f"conv {B}x{H}x{W} {Cin}->{Cout}")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(2, 32, 32, 128, 320, 160), (3, 8, 8, 128, 256, 256),
+                                               (1, 64, 64, 64, 128, 128), (5, 4, 4, 64, 96, 0)])
+def test_conv3x3_256row_tiles(ops, B, H, W, Cin, Cout, bn):
+    from invertible_cd_b200.packing import pack_conv3x3
+    x = _rand(B * H * W, Cin, seed=20)
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=21)
+    bias = torch.randn(Cout, device="cuda")
+    res = _rand(B * H * W, Cout, seed=22)
+    out = ops.conv3x3(x, pack_conv3x3(w), B, H, W, bias=bias, residual=res, force_bn=bn, force_bm=256)
+    _close(out, _conv_ref(x, w, B, H, W, bias) + res.float(), what=f"conv bm256 {B}x{H}x{W} {Cin}->{Cout}")
 
 
 def test_conv3x3_concat_rowvec_residual(ops):

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--only", type=int, default=-1)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--bn", type=int, default=0)
+    ap.add_argument("--bm", type=int, default=0)
     args = ap.parse_args()
     dev = "cuda"
     for idx, (kind, M, N, K, extra) in enumerate(SHAPES):
@@ -48,7 +49,7 @@ def main():
                 w, bias = pack_geglu(w, bias, 256)
             out = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=torch.float16)
             fn = lambda: ops.linear(a, w, bias=bias, residual=res, out=out, geglu=geglu,
-                                    force_bn=256 if geglu else args.bn)
+                                    force_bn=256 if geglu else args.bn, force_bm=0 if geglu else args.bm)
             flops = 2.0 * M * N * K
         else:
             HW = int(extra)
@@ -57,7 +58,7 @@ def main():
             w = (torch.randn(N, 9 * K, device=dev) * (9 * K) ** -0.5).half()
             bias = torch.randn(N, device=dev)
             out = torch.empty(M, N, device=dev, dtype=torch.float16)
-            fn = lambda: ops.conv3x3(x, w, B, HW, HW, bias=bias, out=out, force_bn=args.bn)
+            fn = lambda: ops.conv3x3(x, w, B, HW, HW, bias=bias, out=out, force_bn=args.bn, force_bm=args.bm)
             flops = 2.0 * M * N * K * 9
         for _ in range(3):
             fn()
