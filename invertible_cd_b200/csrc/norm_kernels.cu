@@ -33,19 +33,34 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
   const bool active = r < rows_per_iter;
   const int c = v * 8;
   const int g_lo = c / cpg;
-  __shared__ float s_sum[32], s_sq[32];
-  if (threadIdx.x < 32) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
+  __shared__ float4 s_part[GN_THREADS];        // per-thread (sum_lo, sq_lo, sum_hi, sq_hi): fixed-order reduction
   const int rows_per_chunk = (HW + chunks - 1) / chunks;
   const int p0 = chunk * rows_per_chunk;
   const int p1 = min(HW, p0 + rows_per_chunk);
   float sl = 0.f, ql = 0.f, sh = 0.f, qh = 0.f;
   const int split = (g_lo + 1) * cpg - c;  // elements j < split belong to g_lo, the rest to g_lo + 1
   if (active) {
-    for (int pix = p0 + r; pix < p1; pix += rows_per_iter) {
+    int pix = p0 + r;
+    // two pixels per iteration: two independent 16-byte loads in flight per thread
+    for (; pix + rows_per_iter < p1; pix += 2 * rows_per_iter) {
+      const uint4 raw0 = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, static_cast<long long>(b) * HW + pix, c));
+      const uint4 raw1 =
+          *reinterpret_cast<const uint4*>(gn_vec_ptr(src, static_cast<long long>(b) * HW + pix + rows_per_iter, c));
+      const __half* h0 = reinterpret_cast<const __half*>(&raw0);
+      const __half* h1 = reinterpret_cast<const __half*>(&raw1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = __half2float(h0[j]), x1 = __half2float(h1[j]);
+        if (j < split) {
+          sl += x0 + x1;
+          ql += x0 * x0 + x1 * x1;
+        } else {
+          sh += x0 + x1;
+          qh += x0 * x0 + x1 * x1;
+        }
+      }
+    }
+    for (; pix < p1; pix += rows_per_iter) {
       const uint4 raw = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, static_cast<long long>(b) * HW + pix, c));
       const __half* h = reinterpret_cast<const __half*>(&raw);
 #pragma unroll
@@ -60,18 +75,33 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
         }
       }
     }
-    atomicAdd(&s_sum[g_lo], sl);
-    atomicAdd(&s_sq[g_lo], ql);
-    if (split < 8) {
-      atomicAdd(&s_sum[g_lo + 1], sh);
-      atomicAdd(&s_sq[g_lo + 1], qh);
-    }
   }
+  s_part[threadIdx.x] = make_float4(sl, ql, sh, qh);
   __syncthreads();
   if (threadIdx.x < 32) {
+    // group g gathers, in a fixed order, the "lo" parts of vectors starting inside it and the "hi" parts of the
+    // vectors that straddle into it (deterministic: no floating-point atomics anywhere)
+    const int g = threadIdx.x;
+    const int v_first = max(0, (g * cpg - 7 + 7) / 8 - 1);
+    const int v_last = min(vpr - 1, ((g + 1) * cpg - 1) / 8);
+    float s = 0.f, q = 0.f;
+    for (int vv = v_first; vv <= v_last; ++vv) {
+      const int glo = (vv * 8) / cpg;
+      const int sp = (glo + 1) * cpg - vv * 8;
+      for (int rr = 0; rr < rows_per_iter; ++rr) {
+        const float4 pt = s_part[rr * vpr + vv];
+        if (glo == g) {
+          s += pt.x;
+          q += pt.y;
+        } else if (glo + 1 == g && sp < 8) {
+          s += pt.z;
+          q += pt.w;
+        }
+      }
+    }
     float* o = ws + (static_cast<long long>(b) * chunks + chunk) * 64;
-    o[threadIdx.x] = s_sum[threadIdx.x];
-    o[32 + threadIdx.x] = s_sq[threadIdx.x];
+    o[g] = s;
+    o[32 + g] = q;
   }
 }
 
@@ -112,9 +142,7 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
   const int rows_per_chunk = (HW + apply_chunks - 1) / apply_chunks;
   const int p0 = chunk * rows_per_chunk;
   const int p1 = min(HW, p0 + rows_per_chunk);
-  for (int pix = p0 + r; pix < p1; pix += rows_per_iter) {
-    const long long gp = static_cast<long long>(b) * HW + pix;
-    const uint4 raw = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, gp, c));
+  auto emit = [&](const uint4& raw, long long gp) {
     const __half* h = reinterpret_cast<const __half*>(&raw);
     uint4 outv;
     __half* o = reinterpret_cast<__half*>(&outv);
@@ -125,6 +153,23 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
       o[j] = __float2half_rn(x);
     }
     *reinterpret_cast<uint4*>(y + gp * C + c) = outv;
+  };
+  int pix = p0 + r;
+  for (; pix + 3 * rows_per_iter < p1; pix += 4 * rows_per_iter) {   // four independent 16-byte loads in flight
+    const long long g0 = static_cast<long long>(b) * HW + pix;
+    const long long g1 = g0 + rows_per_iter, g2 = g1 + rows_per_iter, g3 = g2 + rows_per_iter;
+    const uint4 r0 = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, g0, c));
+    const uint4 r1 = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, g1, c));
+    const uint4 r2 = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, g2, c));
+    const uint4 r3 = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, g3, c));
+    emit(r0, g0);
+    emit(r1, g1);
+    emit(r2, g2);
+    emit(r3, g3);
+  }
+  for (; pix < p1; pix += rows_per_iter) {
+    const long long gp = static_cast<long long>(b) * HW + pix;
+    emit(*reinterpret_cast<const uint4*>(gn_vec_ptr(src, gp, c)), gp);
   }
 }
 

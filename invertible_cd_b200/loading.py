@@ -101,12 +101,20 @@ def _load_tensor_file(path):
     return torch.load(path, map_location="cpu")
 
 
-def _unet_source(model_id, w_embed_dim, is_xl):
-    """-> (config, state_dict on CPU, text parts dict)."""
+def _gen_device(device, cfg=None):
+    """Full-size synthetic models (0.86 / 2.6 G parameters) are generated directly on the GPU when there is one;
+    small test models always on the CPU so that the same seed gives the same weights everywhere."""
+    d = torch.device(device)
+    big = cfg is None or arch.count_params(cfg) > 5e8
+    return d if big and d.type == "cuda" and torch.cuda.is_available() else torch.device("cpu")
+
+
+def _unet_source(model_id, w_embed_dim, is_xl, device="cpu"):
+    """-> (config, state_dict, text parts dict)."""
     if isinstance(model_id, str) and model_id.startswith("synthetic"):
         name, seed = _parse_synthetic(model_id)
         cfg = arch.NAMED_CONFIGS[name](time_cond_proj_dim=w_embed_dim if w_embed_dim > 0 else None)
-        return cfg, arch.synthetic_state_dict(cfg, seed=seed), {}
+        return cfg, arch.synthetic_state_dict(cfg, seed=seed, device=_gen_device(device, cfg)), {}
     if not os.path.isdir(model_id):
         raise FileNotFoundError(f"model_id '{model_id}' is neither a local diffusers directory nor 'synthetic:*' "
                                 "(no network access: hub ids cannot be resolved)")
@@ -154,14 +162,15 @@ def _validate(cfg, sd):
                            f"{len(bad)} wrong shape (e.g. {bad[:3]})")
 
 
-def _lora_source(spec, cfg, r):
+def _lora_source(spec, cfg, r, device="cpu"):
     if spec is None:
         return None
     if isinstance(spec, dict):
         return spec
     if isinstance(spec, str) and spec.startswith("synthetic"):
         parts = spec.split(":")
-        return arch.synthetic_lora(cfg, r=r, seed=int(parts[1]) if len(parts) > 1 else 1)
+        return arch.synthetic_lora(cfg, r=r, seed=int(parts[1]) if len(parts) > 1 else 1,
+                                   device=_gen_device(device, cfg))
     return _load_tensor_file(spec)
 
 
@@ -174,7 +183,7 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
     tdtype = torch.float32 if dtype == 'fp32' else torch.float16
     scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
                               set_alpha_to_one=False)
-    cfg, sd, text = _unet_source(model_id, w_embed_dim, is_xl=False)
+    cfg, sd, text = _unet_source(model_id, w_embed_dim, is_xl=False, device=device)
     if w_embed_dim > 0:
         print(f'Forward CD is initialized with guidance embedding, dim {w_embed_dim}')
         if teacher_checkpoint is not None:
@@ -194,14 +203,14 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
             students.append(None)
             continue
         print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')
-        fused = fuse_lora(sd, _lora_source(ckpt, cfg, r), r=r, lora_dtype=torch.float16)
+        fused = fuse_lora(sd, _lora_source(ckpt, cfg, r, device), r=r, lora_dtype=torch.float16)
         students.append(ldm_stable.clone_with_unet(B200UNet(cfg, fused, device)))
     return ldm_stable, students[0], students[1]
 
 
 def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_checkpoint, device="cuda", r=64):
     """-> (stable_pipe, pipe, forw_pipe), as utils/loading.py:93-147 (fp16 base, LoRA kept fp32 for the fuse)."""
-    cfg, sd, text = _unet_source(model_id, 512, is_xl=True)
+    cfg, sd, text = _unet_source(model_id, 512, is_xl=True, device=device)
     if teacher_checkpoint is not None:
         sd = teacher_checkpoint if isinstance(teacher_checkpoint, dict) else _load_tensor_file(teacher_checkpoint)
     sd = OrderedDict((k, v.to(torch.float16)) for k, v in sd.items())
@@ -213,7 +222,7 @@ def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_che
     pipes = []
     for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
         print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')
-        fused = fuse_lora(sd, _lora_source(ckpt, cfg, r), r=r, lora_dtype=torch.float32)
+        fused = fuse_lora(sd, _lora_source(ckpt, cfg, r, device), r=r, lora_dtype=torch.float32)
         pipes.append(stable_pipe.clone_with_unet(B200UNet(cfg, fused, device)))
     return stable_pipe, pipes[0], pipes[1]
 
