@@ -225,9 +225,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
-      const float m_new = fmaxf(m_run, m_tile);
-      const float m_scaled = m_new * p.scale_log2e;
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // 0 on the first tile (m_run = -inf)
+      // Lazy rescale: the reference maximum m_run only moves when the tile maximum exceeds it by more than 2^8
+      // (in the exp2 domain). Until then P <= 256 (exact enough in fp16, fp32 accumulators), so the O / row-sum
+      // rescale in TMEM — a TMEM round trip per tile — is skipped on almost every tile.
+      float alpha = 1.0f;
+      if ((m_tile - m_run) * p.scale_log2e > 8.0f) {
+        alpha = exp2f((m_run - m_tile) * p.scale_log2e);   // 0 on the first tile (m_run = -inf)
+        m_run = m_tile;
+      }
+      const float m_scaled = m_run * p.scale_log2e;
       // pass 2: p = exp2(s*scale*log2e - m) (one FFMA + one MUFU.EX2 per element, packed to fp16 pairs)
       {
         float sa[32], sb[32];
@@ -293,7 +299,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_st_wait();
         }
       }
-      m_run = m_new;
       fence_proxy_async_smem();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
