@@ -42,35 +42,42 @@ template <int D>
 struct AttnCfg {
   static constexpr int DP = (D + 15) / 16 * 16;      // MMA extent along the head dim
   static constexpr int DATOMS = (D + 63) / 64;       // 64-wide (128 B) swizzle atoms along the head dim
-  static constexpr int KV_STAGES = DATOMS >= 3 ? 1 : 2;
-  static constexpr int TILE_BYTES = DATOMS * 16384;  // one Q / K / V tile of 128 rows
-  static constexpr int P_BYTES = 2 * 16384;          // 128 x 128 fp16 probabilities
-  static constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES + 256;
-  static constexpr int TMEM_COLS = (128 + DP + 16) <= 256 ? 256 : 512;   // S | O | 16 row-sum columns
+  static constexpr int BKV = 64;                     // keys per K/V tile
+  static constexpr int KV_STAGES = DATOMS == 1 ? 4 : (DATOMS == 2 ? 4 : 2);
+  static constexpr int Q_BYTES = DATOMS * 16384;     // 128 query rows
+  static constexpr int KV_BYTES = DATOMS * 8192;     // 64 key rows
+  static constexpr int P_BYTES = 2 * 16384;          // double-buffered 128 x 64 fp16 probabilities
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + P_BYTES + 384;   // + barriers, ones tile
+  static constexpr int TMEM_COLS = (128 + DP + 16) <= 256 ? 256 : 512;   // S0 | S1 | O | 16 row-sum columns
   static constexpr int MIN_CTAS = (DATOMS == 1) ? 2 : 1;
 };
 
+// Pipeline (one CTA = one (batch, head, 128-query tile); K/V stream in 64-key tiles through a TMA ring):
+//   S (2 TMEM buffers) and P (2 smem buffers) are double-buffered, so the tensor core computes S_{j+1} = Q.K_{j+1}^T
+//   while the softmax warps are still working on tile j, and P_j.V_j runs while they start on tile j+1.
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2..5: softmax (one thread per query row, S read ONCE from TMEM)
 template <int D>
 __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using Cfg = AttnCfg<D>;
-  constexpr int DP = Cfg::DP, DATOMS = Cfg::DATOMS, ST = Cfg::KV_STAGES;
+  constexpr int DP = Cfg::DP, DATOMS = Cfg::DATOMS, ST = Cfg::KV_STAGES, BKV = Cfg::BKV;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::TILE_BYTES;
-  uint8_t* sV = sK + ST * Cfg::TILE_BYTES;
-  uint8_t* sP = sV + ST * Cfg::TILE_BYTES;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + ST * Cfg::KV_BYTES;
+  uint8_t* sP = sV + ST * Cfg::KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // ST
-  uint64_t* v_full = bars + 1 + ST;   // ST
-  uint64_t* kv_empty = bars + 1 + 2 * ST;  // ST
-  uint64_t* s_full = bars + 1 + 3 * ST;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = s_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 3);
-  uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars) + 128;   // one 8x8 fp16 core matrix of 1.0 (128 B)
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // ST
+  uint64_t* v_full = k_full + ST;          // ST
+  uint64_t* kv_empty = v_full + ST;        // ST   (P.V of the tile consumed K and V)
+  uint64_t* s_full = kv_empty + ST;        // 2    (Q.K^T landed in S[b])
+  uint64_t* p_full = s_full + 2;           // 2    (128 softmax threads wrote P[b]; they are also done reading S[b])
+  uint64_t* pv_done = p_full + 2;          // 2    (P[b].V finished: P[b] reusable, O/L quiescent)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars) + 256;   // one 8x8 fp16 core matrix of 1.0 (128 B)
+  static_assert((1 + 3 * ST + 6) * 8 + 4 <= 256, "barrier block overflows into the ones tile");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = (p.Nq + 127) / 128;
@@ -78,7 +85,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int bh = blockIdx.x / q_tiles;
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qt * 128;
-  const int n_kv = (p.Nk + 127) / 128;
+  const int n_kv = (p.Nk + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -90,9 +97,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
     fence_mbar_init();
   } else if (warp == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -104,82 +113,79 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
   const uint32_t tmem_L = tmem_O + DP;       // row sums: L = P . 1 accumulated by the tensor core
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, Cfg::TILE_BYTES);
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int a = 0; a < DATOMS; ++a) tma_load_4d(sQ + a * 16384, &tmQ, q_full, a * 64, h, q0, b);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
+        mbar_expect_tx(&k_full[stage], Cfg::KV_BYTES);
 #pragma unroll
         for (int a = 0; a < DATOMS; ++a)
-          tma_load_4d(sK + stage * Cfg::TILE_BYTES + a * 16384, &tmK, &k_full[stage], a * 64, h, j * 128, b);
-        mbar_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
+          tma_load_4d(sK + stage * Cfg::KV_BYTES + a * 8192, &tmK, &k_full[stage], a * 64, h, j * BKV, b);
+        mbar_expect_tx(&v_full[stage], Cfg::KV_BYTES);
 #pragma unroll
         for (int a = 0; a < DATOMS; ++a)
-          tma_load_4d(sV + stage * Cfg::TILE_BYTES + a * 16384, &tmV, &v_full[stage], a * 64, h, j * 128, b);
+          tma_load_4d(sV + stage * Cfg::KV_BYTES + a * 8192, &tmV, &v_full[stage], a * 64, h, j * BKV, b);
         if (++stage == ST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, BKV, false, false);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, DP, false, true);
       constexpr uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);
-      mbar_wait(q_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        // S = Q . K_j^T   (S is free: the softmax warps arrived on p_full(j-1) after reading it)
-        mbar_wait(&k_full[stage], phase);
+      // ones operand = a single no-swizzle 8x8 core matrix reused for every (row group, k chunk): LBO=SBO=0
+      const uint64_t ones_desc =
+          (static_cast<uint64_t>((smem_u32(s_ones) >> 4) & 0x3FFF)) | (static_cast<uint64_t>(1) << 46);
+      const uint32_t qa = smem_u32(sQ);
+      auto issue_qk = [&](int jj) {   // S[jj & 1] = Q . K_jj^T
+        const int st = jj % ST;
+        mbar_wait(&k_full[st], (jj / ST) & 1);
         tc_fence_after();
-        {
-          const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + stage * Cfg::TILE_BYTES);
-          int kstep = 0;
+        const uint32_t ka = smem_u32(sK + st * Cfg::KV_BYTES);
+        const uint32_t d_s = tmem_base + (jj & 1) * BKV;
+        int kstep = 0;
 #pragma unroll
-          for (int a = 0; a < DATOMS; ++a) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int kk_n = (DP - a * 64) >= 64 ? 4 : (DP - a * 64) / 16;
+        for (int a = 0; a < DATOMS; ++a) {
+          const int kk_n = (DP - a * 64) >= 64 ? 4 : (DP - a * 64) / 16;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              if (kk < kk_n) {
-                umma_f16_ss(tmem_S, umma_smem_desc(qa + a * 16384 + kk * 32, 16, 1024),
-                            umma_smem_desc(ka + a * 16384 + kk * 32, 16, 1024), idesc_s, kstep != 0);
-                ++kstep;
-              }
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk < kk_n) {
+              umma_f16_ss(d_s, umma_smem_desc(qa + a * 16384 + kk * 32, 16, 1024),
+                          umma_smem_desc(ka + a * 8192 + kk * 32, 16, 1024), idesc_s, kstep != 0);
+              ++kstep;
             }
           }
         }
-        umma_commit(s_full);
-        // O += P_j . V_j
-        mbar_wait(&v_full[stage], phase);
-        mbar_wait(p_full, j & 1);
+        umma_commit(&s_full[jj & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        // S[(j+1)&1] was last read by the softmax of tile j-1, whose p_full we waited for in iteration j-1
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        const int st = j % ST;
+        mbar_wait(&v_full[st], (j / ST) & 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        {
-          const uint32_t pa = smem_u32(sP), va = smem_u32(sV + stage * Cfg::TILE_BYTES);
-          const int valid = min(128, p.Nk - j * 128);
-          const int ksteps = (valid + 15) / 16;
+        const uint32_t pa = smem_u32(sP) + (j & 1) * 16384, va = smem_u32(sV + st * Cfg::KV_BYTES);
+        const int valid = min(BKV, p.Nk - j * BKV);
+        const int ksteps = (valid + 15) / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t pdesc = umma_smem_desc(pa + ks * 32, 16, 1024);
+          umma_f16_ss(tmem_O, pdesc, umma_smem_desc(va + ks * 2048, 8192, 1024), idesc_o, (j | ks) != 0);
           // row sums ride on the tensor core: L[128x16] += P[128xK] . ones[Kx16] (every column = sum_k P)
-          // ones operand = a single no-swizzle 8x8 core matrix reused for every (row group, k chunk): LBO=SBO=0
-          const uint64_t ones_desc = (static_cast<uint64_t>((smem_u32(s_ones) >> 4) & 0x3FFF)) |
-                                     (static_cast<uint64_t>(1) << 46);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t pdesc = umma_smem_desc(pa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-            umma_f16_ss(tmem_O, pdesc, umma_smem_desc(va + ks * 2048, 16384, 1024), idesc_o, (j | ks) != 0);
-            umma_f16_ss(tmem_L, pdesc, ones_desc, idesc_l, (j | ks) != 0);
-          }
+          umma_f16_ss(tmem_L, pdesc, ones_desc, idesc_l, (j | ks) != 0);
         }
-        umma_commit(&kv_empty[stage]);
-        umma_commit(o_full);
-        if (++stage == ST) { stage = 0; phase ^= 1; }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&pv_done[j & 1]);
       }
     }
   } else {
@@ -189,122 +195,85 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int q = q0 + row;
     float m_run = -INFINITY;
+    float alpha_after0 = 1.0f;              // rescale applied after tile 0's P was written (probability capture)
     const uint32_t p_row = smem_u32(sP) + row * 128;
     const int sw = row & 7;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int bsel = j & 1;
+      mbar_wait(&s_full[bsel], (j >> 1) & 1);
       tc_fence_after();
-      const int valid = min(128, p.Nk - j * 128);
-      const bool partial = valid < 128;          // warp-uniform: only the last K/V tile can be partial
-      // pass 1: row maximum (S is re-read from TMEM in pass 2: keeps registers low for 2 CTAs/SM).
-      // TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is reduced.
-      const int nchunks = (valid + 31) >> 5;
-      float m_tile = -INFINITY;
-      {
-        float sa[32], sb[32];
-        tmem_ld32(tmem_S + lane_off, sa);
+      const int valid = min(BKV, p.Nk - j * BKV);
+      float s[64];
+      tmem_ld32(tmem_base + lane_off + bsel * BKV, s);
+      tmem_ld32(tmem_base + lane_off + bsel * BKV + 32, s + 32);
+      tmem_ld_wait();
+      if (valid < BKV) {                    // warp-uniform: only the last K/V tile can be partial
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nchunks) {
-            float* cur = (c & 1) ? sb : sa;
-            float* nxt = (c & 1) ? sa : sb;
-            tmem_ld_wait();
-            if (c + 1 < nchunks) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, nxt);
-            if (partial) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= valid) cur[i] = -INFINITY;
-            }
-            float m0 = fmaxf(cur[0], cur[1]), m1 = fmaxf(cur[2], cur[3]);
-#pragma unroll
-            for (int i = 4; i < 32; i += 4) {
-              m0 = fmaxf(m0, fmaxf(cur[i], cur[i + 1]));
-              m1 = fmaxf(m1, fmaxf(cur[i + 2], cur[i + 3]));
-            }
-            m_tile = fmaxf(m_tile, fmaxf(m0, m1));
-          }
-        }
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) s[i] = -INFINITY;
       }
-      // Lazy rescale: the reference maximum m_run only moves when the tile maximum exceeds it by more than 2^8
-      // (in the exp2 domain). Until then P <= 256 (exact enough in fp16, fp32 accumulators), so the O / row-sum
-      // rescale in TMEM — a TMEM round trip per tile — is skipped on almost every tile.
+      float m0 = fmaxf(s[0], s[1]), m1 = fmaxf(s[2], s[3]);
+#pragma unroll
+      for (int i = 4; i < 64; i += 4) {
+        m0 = fmaxf(m0, fmaxf(s[i], s[i + 1]));
+        m1 = fmaxf(m1, fmaxf(s[i + 2], s[i + 3]));
+      }
+      const float m_tile = fmaxf(m0, m1);
+      // Lazy rescale: the reference maximum only moves when the tile maximum exceeds it by more than 2^8 (exp2
+      // domain); until then P <= 256 (fine in fp16 with fp32 accumulation) and the TMEM round trip is skipped.
       float alpha = 1.0f;
       if ((m_tile - m_run) * p.scale_log2e > 8.0f) {
         alpha = exp2f((m_run - m_tile) * p.scale_log2e);   // 0 on the first tile (m_run = -inf)
         m_run = m_tile;
       }
       const float m_scaled = m_run * p.scale_log2e;
-      // pass 2: p = exp2(s*scale*log2e - m) (one FFMA + one MUFU.EX2 per element, packed to fp16 pairs)
-      {
-        float sa[32], sb[32];
-        tmem_ld32(tmem_S + lane_off, sa);
-        if (j > 0) mbar_wait(o_full, (j - 1) & 1);  // previous P.V finished: P smem and O are ours again
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        // O and L must be quiescent: P_{j-1}.V_{j-1} finished (P_j.V_j cannot start before our p_full arrive)
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t packed[16];
-          if (c < nchunks) {
-            float* cur = (c & 1) ? sb : sa;
-            float* nxt = (c & 1) ? sa : sb;
-            tmem_ld_wait();
-            if (c + 1 < nchunks) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, nxt);
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float x0 = fmaf(cur[i], p.scale_log2e, -m_scaled);
-              float x1 = fmaf(cur[i + 1], p.scale_log2e, -m_scaled);
-              if (partial) {
-                if (c * 32 + i >= valid) x0 = -INFINITY;
-                if (c * 32 + i + 1 >= valid) x1 = -INFINITY;
-              }
-              float e0, e1;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
-              const __half2 e = __floats2half2_rn(e0, e1);
-              packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&e);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) packed[i] = 0u;
-          }
-          const uint32_t atom_base = p_row + (c >> 1) * 16384;
-          const int chunk0 = (c & 1) * 4;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t addr = atom_base + (((chunk0 + cc) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * cc]),
-                         "r"(packed[4 * cc + 1]), "r"(packed[4 * cc + 2]), "r"(packed[4 * cc + 3])
-                         : "memory");
-          }
-        }
-      }
-      // rescale the running output and row sums if any row maximum of this warp moved
-      if (j > 0) {
-        const bool need = alpha != 1.0f;
-        if (__any_sync(0xffffffffu, need)) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < DP + 16; c0 += 16) {
-            float o[16];
-            tmem_ld16(tmem_O + lane_off + c0, o);
-            tmem_ld_wait();
+        for (int c0 = 0; c0 < DP + 16; c0 += 16) {
+          float o[16];
+          tmem_ld16(tmem_O + lane_off + c0, o);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] *= alpha;
-            const uint32_t* r = reinterpret_cast<const uint32_t*>(o);
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
-                "%13, %14, %15, %16};" ::"r"(tmem_O + lane_off + c0),
-                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-                "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-                : "memory");
-          }
-          tmem_st_wait();
+          for (int i = 0; i < 16; ++i) o[i] *= alpha;
+          const uint32_t* r = reinterpret_cast<const uint32_t*>(o);
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+              "%13, %14, %15, %16};" ::"r"(tmem_O + lane_off + c0),
+              "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+              "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+              : "memory");
         }
+        tmem_st_wait();
+        if (j == 1) alpha_after0 = alpha;
+      }
+      // P[bsel] was last read by P_{j-2}.V_{j-2}
+      if (j >= 2) mbar_wait(&pv_done[bsel], ((j - 2) >> 1) & 1);
+      // p = exp2(s*scale*log2e - m): one FFMA + one MUFU.EX2 per element, packed to fp16 pairs -> swizzled smem
+      const uint32_t pbuf = p_row + bsel * 16384;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float e0, e1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(s[cc * 8 + 2 * i], p.scale_log2e, -m_scaled)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s[cc * 8 + 2 * i + 1], p.scale_log2e, -m_scaled)));
+          const __half2 e = __floats2half2_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&e);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pbuf + ((cc ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]),
+                     "r"(pk[2]), "r"(pk[3])
+                     : "memory");
       }
       fence_proxy_async_smem();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[bsel]);
     }
     // epilogue: O / l -> fp16 -> global   (l = row sum accumulated by the ones-MMA)
-    mbar_wait(o_full, (n_kv - 1) & 1);
+    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     float inv;
     {
@@ -313,23 +282,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld_wait();
       inv = 1.f / l16[0];
     }
-    if (p.probs != nullptr && n_kv == 1 && q < p.Nq) {
-      // single K/V tile: emit the normalised probabilities (AttentionStore capture) from the P tile in smem
+    if (p.probs != nullptr && n_kv <= 2 && q < p.Nq) {
+      // <= 128 keys: both P tiles are still in smem -> emit the normalised probabilities (AttentionStore capture)
       __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
-      const int valid = p.Nk;
-      for (int c = 0; c + 1 < valid; c += 2) {
-        const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2;
-        uint32_t u;
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(addr));
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
-        *reinterpret_cast<__half2*>(pr + c) = __floats2half2_rn(f.x * inv, f.y * inv);
-      }
-      if (valid & 1) {
-        const int c = valid - 1;
-        const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2;
+      for (int c = 0; c < p.Nk; ++c) {
+        const int t = c >> 6, cc = c & 63;
+        const uint32_t addr = p_row + t * 16384 + (((cc >> 3) ^ sw) << 4) + (cc & 7) * 2;
         unsigned short u;
         asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
-        pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * inv);
+        const float sc = (t == 0 && n_kv == 2) ? inv * alpha_after0 : inv;
+        pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * sc);
       }
     }
     __half* orow = p.out + (static_cast<long long>(b) * p.Nq + q) * p.out_ld + h * D;
@@ -394,7 +356,8 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   if ((D % 8) != 0) return set_error("icd_attention: head dim must be a multiple of 8");
   CUtensorMap tq, tk, tv;
   // tensor maps over [B][N][H][D] as dims (d, head, token, batch): strides grow monotonically
-  const uint32_t box[4] = {64, 1, 128, 1};
+  const uint32_t box[4] = {64, 1, 128, 1};      // Q: 128 query rows
+  const uint32_t boxkv[4] = {64, 1, 64, 1};     // K, V: 64 keys per tile
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nq, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)q_ld * 2, (uint64_t)q_ld * Nq * 2};
@@ -403,9 +366,9 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nk, (uint64_t)B};
     const uint64_t strk[3] = {(uint64_t)D * 2, (uint64_t)k_ld * 2, (uint64_t)k_ld * Nk * 2};
-    if (make_tmap_4d(&tk, k, dims, strk, box, 128)) return 1;
+    if (make_tmap_4d(&tk, k, dims, strk, boxkv, 128)) return 1;
     const uint64_t strv[3] = {(uint64_t)D * 2, (uint64_t)v_ld * 2, (uint64_t)v_ld * Nk * 2};
-    if (make_tmap_4d(&tv, v, dims, strv, box, 128)) return 1;
+    if (make_tmap_4d(&tv, v, dims, strv, boxkv, 128)) return 1;
   }
   AttnParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
