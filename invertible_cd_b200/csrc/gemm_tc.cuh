@@ -77,7 +77,8 @@ struct GemmCfg {
   static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;             // double-buffer when TMEM allows
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;                      // power of two in [64, 512]
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + R_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int THREADS = (EPI == EPI_STAGED_RES) ? 224 : 192;  // + residual-producer warp
+  static constexpr int EPI_THREADS = 256;            // 8 epilogue warps: two per TMEM lane quadrant
+  static constexpr int THREADS = 64 + EPI_THREADS + ((EPI == EPI_STAGED_RES) ? 32 : 0);  // + residual-producer warp
 };
 
 template <int BM, int BN, int EPI>
@@ -116,11 +117,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], Cfg::EPI_THREADS);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&res_full[i], 1);
-      mbar_init(&res_empty[i], 128);
+      mbar_init(&res_empty[i], Cfg::EPI_THREADS);
     }
     tma_prefetch_desc(&tmOut);
     tma_prefetch_desc(&tmRes);
@@ -235,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // ------------------------------------------------------------------ residual producer (EPI_STAGED_RES only)
     if constexpr (EPI == EPI_STAGED_RES) {
       if (lane == 0) {
@@ -264,7 +265,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     // NOTE: loops are deliberately rolled (#pragma unroll 1) — a fully unrolled epilogue is ~200 KB of SASS and
     // runs out of the instruction cache (measured: 21k cycles per tile, ncu profiles/r1_c_*).
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int part = (warp - 2) >> 2;    // the two warps of a quadrant split every 64-column unit (32 columns each)
     const int row_in_tile = quad * 32 + lane;
     int iter = 0;
     if constexpr (EPI != EPI_DIRECT) {
@@ -294,12 +296,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int row = mt * BM + half * 128 + row_in_tile;
         const bool row_ok = row < p.M;
         const __half* rp = p.residual + static_cast<long long>(row) * p.ldr + n_out0;
-        uint4 rcur[8], rnxt[8];
+        uint4 rcur[4], rnxt[4];
         auto load_res = [&](uint4* dst, int u) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             dst[i] = make_uint4(0, 0, 0, 0);
-            const int c = u * 64 + i * 8;
+            const int c = u * 64 + part * 32 + i * 8;
             if (has_res && row_ok && c < outw && n_out0 + c < n_out_total)
               dst[i] = __ldg(reinterpret_cast<const uint4*>(rp + c));
           }
@@ -321,10 +323,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if constexpr (EPI == EPI_STAGED_RES) mbar_wait(&res_full[unit & 1], (unit >> 1) & 1);
           // staging buffer (unit & 1) was last used by unit-2: its TMA store must have finished reading smem
           if (leader) bulk_wait_read1();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, Cfg::EPI_THREADS);
           if constexpr (GEGLU) {
 #pragma unroll 1
-            for (int c16 = 0; c16 < unit_cols; c16 += 16) {
+            for (int c16 = part * 32; c16 < min(unit_cols, part * 32 + 32); c16 += 16) {
               const int col_t = u * 64 + c16;
               float hv[16], gv[16];
               tmem_ld16(t_addr + col_t, hv);
@@ -353,8 +355,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                            "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
             }
           } else {
-#pragma unroll
-            for (int h32 = 0; h32 < 2; ++h32) {
+            {
+              const int h32 = part;
               const int c0 = h32 * 32;
               const int col_t = u * 64 + c0;         // output column within the tile
               const int ncol = n_out0 + col_t;       // global output column
@@ -385,7 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                  : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w)
                                  : "r"(ra));
                   } else {
-                    rr = rcur[h32 * 4 + cc];
+                    rr = rcur[cc];
                   }
                   const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
                   uint32_t o[4];
@@ -405,7 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               mbar_arrive(&res_empty[unit & 1]);
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) rcur[i] = rnxt[i];
+              for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
             }
           }
           if (u == units - 1 && half == HALVES - 1) {   // all TMEM reads of this accumulator are done
@@ -413,7 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_arrive(&tmem_empty[acc]);
           }
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
+          named_bar_sync(2, Cfg::EPI_THREADS);
           if (leader) {
 #pragma unroll
             for (int h32 = 0; h32 < 2; ++h32) {
@@ -453,7 +455,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 : nullptr;
         const int n0 = nt * BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = part * 16; c0 < BN; c0 += 32) {
           if (n0 + c0 >= p.N) break;  // warp-uniform
           float v[16];
           tmem_ld16(t_addr + c0, v);
