@@ -41,22 +41,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
   const int split = (g_lo + 1) * cpg - c;  // elements j < split belong to g_lo, the rest to g_lo + 1
   if (active) {
     int pix = p0 + r;
-    // two pixels per iteration: two independent 16-byte loads in flight per thread
-    for (; pix + rows_per_iter < p1; pix += 2 * rows_per_iter) {
-      const uint4 raw0 = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, static_cast<long long>(b) * HW + pix, c));
-      const uint4 raw1 =
-          *reinterpret_cast<const uint4*>(gn_vec_ptr(src, static_cast<long long>(b) * HW + pix + rows_per_iter, c));
-      const __half* h0 = reinterpret_cast<const __half*>(&raw0);
-      const __half* h1 = reinterpret_cast<const __half*>(&raw1);
+    // four pixels per iteration: four independent 16-byte loads in flight per thread
+    for (; pix + 3 * rows_per_iter < p1; pix += 4 * rows_per_iter) {
+      uint4 raw[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float x0 = __half2float(h0[j]), x1 = __half2float(h1[j]);
-        if (j < split) {
-          sl += x0 + x1;
-          ql += x0 * x0 + x1 * x1;
-        } else {
-          sh += x0 + x1;
-          qh += x0 * x0 + x1 * x1;
+      for (int u = 0; u < 4; ++u)
+        raw[u] = *reinterpret_cast<const uint4*>(
+            gn_vec_ptr(src, static_cast<long long>(b) * HW + pix + u * rows_per_iter, c));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half* h = reinterpret_cast<const __half*>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x = __half2float(h[j]);
+          if (j < split) {
+            sl += x;
+            ql += x * x;
+          } else {
+            sh += x;
+            qh += x * x;
+          }
         }
       }
     }
@@ -270,13 +274,13 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   if (cpg < 8) return set_error("icd_groupnorm: channels per group < 8 unsupported");
   GnSrc src{reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), C0, x1 != nullptr ? C1 : 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int chunks = (2 * sm_count() + B - 1) / B;
+  int chunks = (4 * sm_count() + B - 1) / B;
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
   if (chunks > HW) chunks = HW;
   if (chunks < 1) chunks = 1;
   gn_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, st>>>(src, HW, cpg, chunks, stats_ws);
   if (check_launch("gn_stats")) return 1;
-  int apply_chunks = (4 * sm_count() + B - 1) / B;
+  int apply_chunks = (6 * sm_count() + B - 1) / B;
   if (apply_chunks > HW) apply_chunks = HW;
   if (apply_chunks < 1) apply_chunks = 1;
   gn_apply_kernel<<<dim3(apply_chunks, B), GN_THREADS, 0, st>>>(src, reinterpret_cast<__half*>(y), HW, cpg, chunks,
