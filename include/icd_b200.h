@@ -69,6 +69,9 @@ typedef struct IcdGemm {
   int geglu;               /* B rows packed per BN tile as [h | gate]; out[:, j] = h_j * gelu(g_j); N counts packed rows */
   int force_bn;            /* 0 = heuristic, else 64/128/160/256 */
   int force_bm;            /* 0 = heuristic, else 128/256 (rows per CTA tile) */
+  int force_splits;        /* 0 = heuristic, else split-K factor (needs ws) */
+  void* ws;                /* optional fp32 split-K workspace (device), may be NULL */
+  long long ws_bytes;
   /* fused consistency update on the (transposed, fp32) output — utils/generation.py:136-155 */
   const float* upd_x;
   float* upd_out;

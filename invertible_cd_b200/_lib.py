@@ -29,7 +29,8 @@ class IcdGemm(C.Structure):
         ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rows_per_img", C.c_int),
         ("ldv", C.c_int), ("residual", C.c_void_p), ("ldr", C.c_longlong), ("res_zstride", C.c_longlong),
         ("out", C.c_void_p), ("ldc", C.c_longlong), ("out_z1_stride", C.c_longlong), ("out_z2_stride", C.c_longlong), ("out_imgstride", C.c_longlong),
-        ("out_fp32", C.c_int), ("out_mode", C.c_int), ("geglu", C.c_int), ("force_bn", C.c_int), ("force_bm", C.c_int),
+        ("out_fp32", C.c_int), ("out_mode", C.c_int), ("geglu", C.c_int), ("force_bn", C.c_int), ("force_bm", C.c_int), ("force_splits", C.c_int),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_longlong),
         ("upd_x", C.c_void_p), ("upd_out", C.c_void_p),
         ("alpha_t", C.c_float), ("sigma_t", C.c_float), ("alpha_s", C.c_float), ("sigma_s", C.c_float),
     ]

@@ -27,7 +27,7 @@
 namespace icd {
 
 int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_b[3],
-                 const uint32_t box[4], int swizzle_bytes);
+                 const uint32_t box[4], int swizzle_bytes, int elem_bytes);
 
 struct AttnParams {
   int B, H, Nq, Nk;
@@ -144,24 +144,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ones operand = a single no-swizzle 8x8 core matrix reused for every (row group, k chunk): LBO=SBO=0
       const uint64_t ones_desc =
           (static_cast<uint64_t>((smem_u32(s_ones) >> 4) & 0x3FFF)) | (static_cast<uint64_t>(1) << 46);
-      const uint32_t qa = smem_u32(sQ);
+      // smem descriptors are formed by adding constants to precomputed 32-bit low words (building one from an
+      // address costs ~120 cycles of dependent uniform-datapath ops: more than these small MMAs take)
+      const uint64_t desc_hi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      const uint32_t q_lo0 = ((smem_u32(sQ) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t k_lo0 = ((smem_u32(sK) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t p_lo0 = ((smem_u32(sP) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t v_lo0 = ((smem_u32(sV) >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);   // MN-major: LBO = 8 KB
       auto issue_qk = [&](int jj) {   // S[jj & 1] = Q . K_jj^T
         const int st = jj % ST;
         mbar_wait(&k_full[st], (jj / ST) & 1);
         tc_fence_after();
-        const uint32_t ka = smem_u32(sK + st * Cfg::KV_BYTES);
+        const uint32_t k_lo = k_lo0 + st * (Cfg::KV_BYTES >> 4);
         const uint32_t d_s = tmem_base + (jj & 1) * BKV;
-        int kstep = 0;
 #pragma unroll
         for (int a = 0; a < DATOMS; ++a) {
           const int kk_n = (DP - a * 64) >= 64 ? 4 : (DP - a * 64) / 16;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            if (kk < kk_n) {
-              umma_f16_ss(d_s, umma_smem_desc(qa + a * 16384 + kk * 32, 16, 1024),
-                          umma_smem_desc(ka + a * 8192 + kk * 32, 16, 1024), idesc_s, kstep != 0);
-              ++kstep;
-            }
+            if (kk < kk_n)
+              umma_f16_ss(d_s, desc_hi | (q_lo0 + a * (16384u >> 4) + kk * 2u),
+                          desc_hi | (k_lo + a * (8192u >> 4) + kk * 2u), idesc_s, (a | kk) != 0);
           }
         }
         umma_commit(&s_full[jj & 1]);
@@ -175,12 +178,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(&v_full[st], (j / ST) & 1);
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP) + (j & 1) * 16384, va = smem_u32(sV + st * Cfg::KV_BYTES);
+        const uint32_t p_lo = p_lo0 + (j & 1) * (16384u >> 4), v_lo = v_lo0 + st * (Cfg::KV_BYTES >> 4);
         const int valid = min(BKV, p.Nk - j * BKV);
         const int ksteps = (valid + 15) / 16;
+#pragma unroll 4
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t pdesc = umma_smem_desc(pa + ks * 32, 16, 1024);
-          umma_f16_ss(tmem_O, pdesc, umma_smem_desc(va + ks * 2048, 8192, 1024), idesc_o, (j | ks) != 0);
+          const uint64_t pdesc = desc_hi | (p_lo + ks * 2u);
+          umma_f16_ss(tmem_O, pdesc, desc_hi | (v_lo + ks * (2048u >> 4)), idesc_o, (j | ks) != 0);
           // row sums ride on the tensor core: L[128x16] += P[128xK] . ones[Kx16] (every column = sum_k P)
           umma_f16_ss(tmem_L, pdesc, ones_desc, idesc_l, (j | ks) != 0);
         }
@@ -361,14 +365,14 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nq, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)q_ld * 2, (uint64_t)q_ld * Nq * 2};
-    if (make_tmap_4d(&tq, q, dims, str, box, 128)) return 1;
+    if (make_tmap_4d(&tq, q, dims, str, box, 128, 2)) return 1;
   }
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)Nk, (uint64_t)B};
     const uint64_t strk[3] = {(uint64_t)D * 2, (uint64_t)k_ld * 2, (uint64_t)k_ld * Nk * 2};
-    if (make_tmap_4d(&tk, k, dims, strk, boxkv, 128)) return 1;
+    if (make_tmap_4d(&tk, k, dims, strk, boxkv, 128, 2)) return 1;
     const uint64_t strv[3] = {(uint64_t)D * 2, (uint64_t)v_ld * 2, (uint64_t)v_ld * Nk * 2};
-    if (make_tmap_4d(&tv, v, dims, strv, boxkv, 128)) return 1;
+    if (make_tmap_4d(&tv, v, dims, strv, boxkv, 128, 2)) return 1;
   }
   AttnParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;

@@ -52,13 +52,13 @@ static std::mutex g_tmap_mu;
 
 // fp16, rank-4, 128B (or 64B) swizzle. dims/box in elements, strides (dims 1..3) in bytes.
 int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_b[3],
-                 const uint32_t box[4], int swizzle_bytes) {
+                 const uint32_t box[4], int swizzle_bytes, int elem_bytes) {
   TmapKey key;
   key.v[0] = reinterpret_cast<uint64_t>(ptr);
   for (int i = 0; i < 4; ++i) key.v[1 + i] = dims[i];
   for (int i = 0; i < 3; ++i) key.v[5 + i] = strides_b[i];
   for (int i = 0; i < 4; ++i) key.v[8 + i] = box[i];
-  key.v[12] = static_cast<uint64_t>(swizzle_bytes);
+  key.v[12] = static_cast<uint64_t>(swizzle_bytes) | (static_cast<uint64_t>(elem_bytes) << 16);
   {
     std::lock_guard<std::mutex> lk(g_tmap_mu);
     auto it = g_tmap_cache.find(key);
@@ -77,7 +77,7 @@ int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], cons
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {1, 1, 1, 1};
   alignas(64) CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = fn(&m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -104,12 +104,13 @@ int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], cons
 // Tile-shape heuristic. Every operand byte is fetched from L2 by each CTA that needs it, and a 128x160 tile at
 // full tensor rate would need ~31 TB/s of L2->SM traffic (measured cap ~12 TB/s, profiles/r1_c_*), so the model
 // charges each K block max(MMA time, L2 time) and prefers 256-row tiles (two MMA halves share one B tile).
-struct TileChoice { int bm, bn; };
-static TileChoice pick_tile(int M, int N, int Z, int num_kb, int geglu, int b_mn_major, int force_bn, int force_bm) {
+struct TileChoice { int bm, bn, splits; };
+static TileChoice pick_tile(int M, int N, int Z, int num_kb, int geglu, int b_mn_major, int force_bn, int force_bm,
+                            int max_splits = 1) {
   const int sms = sm_count();
   const int bns[4] = {256, 160, 128, 64};
   const int bms[2] = {128, 256};
-  TileChoice best{128, 128};
+  TileChoice best{128, 128, 1};
   double best_cost = 1e30;
   for (int bi = 0; bi < 2; ++bi) {
     const int bm = bms[bi];
@@ -124,18 +125,24 @@ static TileChoice pick_tile(int M, int N, int Z, int num_kb, int geglu, int b_mn
         if (bn > 64 && N <= bn / 2) continue;  // mostly-empty tile
       }
       const long long tiles = static_cast<long long>((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Z;
-      const long long waves = (tiles + sms - 1) / sms;
       const double mma = bm * bn / 64.0;               // cycles per 64-deep K block
       const double l2 = 3.0 * (bm + bn);               // (bm+bn) * 128 B / ~42.5 B/clk/SM
-      const double mainloop = num_kb * (mma > l2 ? mma : l2) + 1500.0;
       const double epi = (bm / 128) * (600.0 + 6.0 * bn) * (geglu ? 3.0 : 1.0);
       const int half_stride = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
       const bool dbl = 2 * (bm / 128) * half_stride <= 512;
-      const double per_tile = dbl ? (mainloop > epi ? mainloop : epi) : mainloop + epi;
-      const double cost = waves * per_tile + (dbl ? epi : 0.0);
-      if (cost < best_cost) {
-        best_cost = cost;
-        best = TileChoice{bm, bn};
+      for (int sp = 1; sp <= max_splits; ++sp) {
+        if (sp > 1 && (tiles * sp > sms || num_kb / sp < 8)) break;   // split-K only to fill idle SMs
+        const int kbs = (num_kb + sp - 1) / sp;
+        const long long waves = (tiles * sp + sms - 1) / sms;
+        const double mainloop = kbs * (mma > l2 ? mma : l2) + 1500.0;
+        const double per_tile = dbl ? (mainloop > epi ? mainloop : epi) : mainloop + epi;
+        double cost = waves * per_tile + (dbl ? epi : 0.0);
+        // fp32 partials written + re-read by the reduce kernel (~3400 B/clk of HBM), plus its launch
+        if (sp > 1) cost += 5000.0 + static_cast<double>(sp + 1) * M * N * 4.0 / 3400.0;
+        if (cost < best_cost) {
+          best_cost = cost;
+          best = TileChoice{bm, bn, sp};
+        }
       }
     }
   }
@@ -162,12 +169,61 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   return 0;
 }
 
+// split-K pass 2: out = fp16( alpha * sum_s ws[s] + bias + rowvec[img] + residual ), 8 columns per thread
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float alpha, const float* __restrict__ bias,
+                     const float* __restrict__ rowvec, int rows_per_img, int ldv, const __half* __restrict__ res,
+                     long long ldr, __half* __restrict__ out, long long ldc) {
+  const int nv = N >> 3;
+  const long long total = static_cast<long long>(M) * nv;
+  const long long mn = static_cast<long long>(M) * N;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / nv);
+    const int n = static_cast<int>(i - static_cast<long long>(m) * nv) << 3;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < splits; ++s) {
+      const float4* w = reinterpret_cast<const float4*>(ws + s * mn + static_cast<long long>(m) * N + n);
+      const float4 a = w[0], b = w[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    const float* rv = rowvec != nullptr ? rowvec + static_cast<long long>(m / rows_per_img) * ldv + n : nullptr;
+    uint4 rr = make_uint4(0, 0, 0, 0);
+    if (res != nullptr) rr = *reinterpret_cast<const uint4*>(res + static_cast<long long>(m) * ldr + n);
+    const __half* rh = reinterpret_cast<const __half*>(&rr);
+    uint4 o;
+    __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = acc[j] * alpha;
+      if (bias != nullptr) x += bias[n + j];
+      if (rv != nullptr) x += rv[j];
+      x += __half2float(rh[j]);
+      oh[j] = __float2half_rn(x);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<long long>(m) * ldc + n) = o;
+  }
+}
+
+static int launch_splitk_reduce(const float* ws, int splits, int M, int N, float alpha, const float* bias,
+                                const float* rowvec, int rows_per_img, int ldv, const __half* res, long long ldr,
+                                __half* out, long long ldc, cudaStream_t st) {
+  const long long total = static_cast<long long>(M) * (N / 8);
+  long long grid = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  splitk_reduce_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(ws, splits, M, N, alpha, bias, rowvec,
+                                                                    rows_per_img, ldv, res, ldr, out, ldc);
+  return check_launch("splitk_reduce");
+}
+
 }  // namespace icd
 
 using namespace icd;
 
 extern "C" int icd_gemm_pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn) {
-  return pick_tile(M, N, Z, 16, geglu, b_mn_major, force_bn, 0).bn;
+  return pick_tile(M, N, Z, 16, geglu, b_mn_major, force_bn, 0, 1).bn;
 }
 
 extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
@@ -177,7 +233,23 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   const int kb_est = ((g->K0 + 63) / 64 + (g->a1 != nullptr ? (g->K1 + 63) / 64 : 0)) * (g->a_mode == 1 ? 9 : 1);
   // small-K GEMMs with a residual use the TMA-streamed residual variant, which exists for 128-row tiles only
   const int fbm = (g->force_bm == 0 && g->residual != nullptr && kb_est <= 24) ? 128 : g->force_bm;
-  const TileChoice tc = pick_tile(g->M, g->N, g->Z, kb_est, g->geglu, g->b_mn_major, g->force_bn, fbm);
+  // split-K (fp32 partials in the caller's workspace + a reduce kernel) for few-tile, deep-K problems
+  const bool split_ok = g->ws != nullptr && !g->geglu && !g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR &&
+                        g->Z == 1 && (g->N % 16) == 0 && g->upd_x == nullptr && (g->ldc % 8) == 0 &&
+                        (g->residual == nullptr || (g->ldr % 8) == 0);
+  int max_splits = 1;
+  if (split_ok) {
+    const long long per = static_cast<long long>(g->M) * g->N * 4;
+    max_splits = static_cast<int>(g->ws_bytes / (per > 0 ? per : 1));
+    if (max_splits > 16) max_splits = 16;
+    if (max_splits < 1) max_splits = 1;
+  }
+  max_splits = 1;   // measured (tools/splitk_probe.py): no gain yet on B200 for the 8x8-level shapes -> opt-in only
+  TileChoice tc = pick_tile(g->M, g->N, g->Z, kb_est, g->geglu, g->b_mn_major, g->force_bn, fbm, max_splits);
+  if (g->force_splits > 0) {
+    tc = pick_tile(g->M, g->N, g->Z, kb_est, g->geglu, g->b_mn_major, g->force_bn, fbm, 1);
+    if (split_ok && static_cast<long long>(g->force_splits) * g->M * g->N * 4 <= g->ws_bytes) tc.splits = g->force_splits;
+  }
   const int bn = tc.bn, bm = tc.bm;
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error("icd_gemm: unsupported BN");
   if (g->b_mn_major && (bn % 64) != 0) return set_error("icd_gemm: MN-major B needs BN multiple of 64");
@@ -197,6 +269,7 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   const int kb1 = g->a1 != nullptr ? (g->K1 + 63) / 64 : 0;
   p.kb_split = kb0;
   p.kb_per_tap = kb0 + kb1;
+  p.splits = 1;
 
   CUtensorMap tmA0, tmA1, tmB;
   if (g->a_mode == GEMM_A_CONV3X3) {
@@ -220,12 +293,12 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     {
       const uint64_t dims[4] = {(uint64_t)g->K0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       const uint64_t str[3] = {(uint64_t)g->a0_ld * 2, (uint64_t)g->a0_ld * W * 2, (uint64_t)g->a0_ld * hw * 2};
-      if (make_tmap_4d(&tmA0, g->a0, dims, str, box, 128)) return 1;
+      if (make_tmap_4d(&tmA0, g->a0, dims, str, box, 128, 2)) return 1;
     }
     if (g->a1 != nullptr) {
       const uint64_t dims[4] = {(uint64_t)g->K1, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       const uint64_t str[3] = {(uint64_t)g->a1_ld * 2, (uint64_t)g->a1_ld * W * 2, (uint64_t)g->a1_ld * hw * 2};
-      if (make_tmap_4d(&tmA1, g->a1, dims, str, box, 128)) return 1;
+      if (make_tmap_4d(&tmA1, g->a1, dims, str, box, 128, 2)) return 1;
     } else {
       tmA1 = tmA0;
     }
@@ -238,14 +311,14 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
       const uint64_t s1 = g->a_z1_stride > 0 ? (uint64_t)g->a_z1_stride * 2 : (uint64_t)g->a0_ld * 2;
       const uint64_t s2 = g->a_z2_stride > 0 ? (uint64_t)g->a_z2_stride * 2 : s1;
       const uint64_t str[3] = {(uint64_t)g->a0_ld * 2, s1, s2};
-      if (make_tmap_4d(&tmA0, g->a0, dims, str, box, 128)) return 1;
+      if (make_tmap_4d(&tmA0, g->a0, dims, str, box, 128, 2)) return 1;
     }
     if (g->a1 != nullptr) {
       const uint64_t dims[4] = {(uint64_t)g->K1, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
       const uint64_t s1 = g->a_z1_stride > 0 ? (uint64_t)g->a_z1_stride * 2 : (uint64_t)g->a1_ld * 2;
       const uint64_t s2 = g->a_z2_stride > 0 ? (uint64_t)g->a_z2_stride * 2 : s1;
       const uint64_t str[3] = {(uint64_t)g->a1_ld * 2, s1, s2};
-      if (make_tmap_4d(&tmA1, g->a1, dims, str, box, 128)) return 1;
+      if (make_tmap_4d(&tmA1, g->a1, dims, str, box, 128, 2)) return 1;
     } else {
       tmA1 = tmA0;
     }
@@ -262,11 +335,11 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     if (g->b_mn_major) {
       const uint64_t dims[4] = {(uint64_t)g->N, kreal, batched_b ? (uint64_t)p.ZB1 : 1, batched_b ? z2 : 1};
       const uint32_t box[4] = {64, 64, 1, 1};
-      if (make_tmap_4d(&tmB, g->b, dims, str, box, 128)) return 1;
+      if (make_tmap_4d(&tmB, g->b, dims, str, box, 128, 2)) return 1;
     } else {
       const uint64_t dims[4] = {kreal, (uint64_t)g->N, batched_b ? (uint64_t)p.ZB1 : 1, batched_b ? z2 : 1};
       const uint32_t box[4] = {64, (uint32_t)bn, 1, 1};
-      if (make_tmap_4d(&tmB, g->b, dims, str, box, 128)) return 1;
+      if (make_tmap_4d(&tmB, g->b, dims, str, box, 128, 2)) return 1;
     }
     p.b_batched = batched_b ? 1 : 0;
   }
@@ -293,6 +366,45 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   if (p.upd_x != nullptr && !(p.out_fp32 && p.out_mode == GEMM_OUT_TRANSPOSED))
     return set_error("icd_gemm: fused update needs fp32 transposed output");
 
+  p.kb_per_split = p.num_kb;   // single split: the whole K range (num_kb is final here)
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ICD_LAUNCH(BM_, BN_, EPI_) return launch<BM_, BN_, EPI_>(tmA0, tmA1, tmB, tmOut, tmRes, p, st)
+#define ICD_LAUNCH_BN(BM_, EPI_)                 \
+  switch (bn) {                                  \
+    case 64: ICD_LAUNCH(BM_, 64, EPI_);          \
+    case 128: ICD_LAUNCH(BM_, 128, EPI_);        \
+    case 160: ICD_LAUNCH(BM_, 160, EPI_);        \
+    default: ICD_LAUNCH(BM_, 256, EPI_);         \
+  }
+  if (tc.splits > 1) {
+    // pass 1: raw fp32 partial products of each K range -> ws[split][M][N]; pass 2: reduce + fused epilogue
+    GemmParams q = p;
+    q.splits = tc.splits;
+    q.kb_per_split = (p.num_kb + tc.splits - 1) / tc.splits;
+    q.split_out_stride = static_cast<long long>(g->M) * g->N;
+    q.alpha = 1.0f;
+    q.bias = nullptr; q.rowvec = nullptr; q.residual = nullptr;
+    q.out = g->ws; q.ldc = g->N; q.out_z1_stride = 0; q.out_z2_stride = 0;
+    q.out_fp32 = 1; q.out_mode = GEMM_OUT_ROWMAJOR; q.epi_tma = 0; q.res_tma = 0;
+    q.split_z = 1;
+    CUtensorMap tmOut, tmRes = tmB;
+    {   // ws viewed as [splits][M][N] fp32: 4th TMA coordinate = split
+      const uint32_t box[4] = {32, 128, 1, 1};
+      const uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->M, 1, (uint64_t)tc.splits};
+      const uint64_t str[3] = {(uint64_t)g->N * 4, (uint64_t)g->N * 4 * g->M, (uint64_t)g->N * 4 * g->M};
+      if (make_tmap_4d(&tmOut, g->ws, dims, str, box, 128, 4)) return 1;
+    }
+    auto pass1 = [&]() -> int {
+      const GemmParams& p = q;
+      if (bm == 256) { ICD_LAUNCH_BN(256, EPI_STAGED_F32) }
+      ICD_LAUNCH_BN(128, EPI_STAGED_F32)
+    };
+    if (pass1()) return 1;
+    return launch_splitk_reduce(reinterpret_cast<const float*>(g->ws), tc.splits, g->M, g->N, g->alpha, g->bias,
+                                g->rowvec, p.rows_per_img, g->ldv, reinterpret_cast<const __half*>(g->residual),
+                                g->ldr, reinterpret_cast<__half*>(g->out), g->ldc, st);
+  }
+
   // staged TMA-store epilogue whenever the output is an fp16 row-major matrix TMA can address
   CUtensorMap tmOut = tmB, tmRes = tmB;
   const bool aligned = (g->ldc % 8) == 0 && (reinterpret_cast<uint64_t>(g->out) & 15) == 0 &&
@@ -310,23 +422,28 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     const uint64_t s1 = g->out_z1_stride > 0 ? (uint64_t)g->out_z1_stride * 2 : (uint64_t)g->ldc * 2;
     const uint64_t s2 = g->out_z2_stride > 0 ? (uint64_t)g->out_z2_stride * 2 : s1;
     const uint64_t str[3] = {(uint64_t)g->ldc * 2, s1, s2};
-    if (make_tmap_4d(&tmOut, g->out, dims, str, box, 64)) return 1;
+    if (make_tmap_4d(&tmOut, g->out, dims, str, box, 64, 2)) return 1;
     p.res_tma = g->residual != nullptr ? 1 : 0;
     if (g->residual != nullptr) {
       const uint64_t rdims[4] = {n_out, (uint64_t)g->M, 1, 1};
       const uint64_t rstr[3] = {(uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2};
-      if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, box, 64)) return 1;
+      if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, box, 64, 2)) return 1;
     }
   }
 
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define ICD_LAUNCH(BM_, BN_, EPI_) return launch<BM_, BN_, EPI_>(tmA0, tmA1, tmB, tmOut, tmRes, p, st)
-#define ICD_LAUNCH_BN(BM_, EPI_)                 \
-  switch (bn) {                                  \
-    case 64: ICD_LAUNCH(BM_, 64, EPI_);          \
-    case 128: ICD_LAUNCH(BM_, 128, EPI_);        \
-    case 160: ICD_LAUNCH(BM_, 160, EPI_);        \
-    default: ICD_LAUNCH(BM_, 256, EPI_);         \
+  if (g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR && g->residual == nullptr && g->rowvec == nullptr &&
+      (g->N % 16) == 0 && (g->ldc % 4) == 0 && (reinterpret_cast<uint64_t>(g->out) & 15) == 0 &&
+      (g->out_z1_stride % 4) == 0 && (g->out_z2_stride % 4) == 0) {
+    const uint64_t z2 = (uint64_t)((g->Z + p.ZA1 - 1) / p.ZA1);
+    const uint32_t box[4] = {32, 128, 1, 1};
+    const uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
+    const uint64_t s1 = g->out_z1_stride > 0 ? (uint64_t)g->out_z1_stride * 4 : (uint64_t)g->ldc * 4;
+    const uint64_t s2 = g->out_z2_stride > 0 ? (uint64_t)g->out_z2_stride * 4 : s1;
+    const uint64_t str[3] = {(uint64_t)g->ldc * 4, s1, s2};
+    if (make_tmap_4d(&tmOut, g->out, dims, str, box, 128, 4)) return 1;
+    p.split_z = 0;
+    if (bm == 256) { ICD_LAUNCH_BN(256, EPI_STAGED_F32) }
+    ICD_LAUNCH_BN(128, EPI_STAGED_F32)
   }
   if (g->geglu) {
     if (bm != 128) return set_error("icd_gemm: GEGLU uses 128-row tiles");

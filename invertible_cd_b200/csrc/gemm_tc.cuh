@@ -31,6 +31,10 @@ struct GemmParams {
   int Z, ZA1, ZB1;   // batch entries; A coords are (k, m, z % ZA1, z / ZA1), B coords (k, n, z % ZB1, z / ZB1)
   int b_mn_major;    // B tile is [K][N] (N contiguous) instead of [N][K]
   int b_batched;     // B has batch coordinates (else every z reads the same B)
+  int splits;        // split-K: each tile is computed by `splits` CTAs over disjoint K ranges (fp32 partials)
+  int kb_per_split;
+  long long split_out_stride;  // elements between the partial outputs of consecutive splits
+  int split_z;                 // staged fp32 epilogue: split s is stored at 4th TMA coordinate s * split_z
   // conv geometry (pixels of one 128-row M tile = tile_b images x tile_h rows x tile_w cols)
   int H, W, tile_w, tile_h, tile_b;
   // epilogue
@@ -59,7 +63,7 @@ struct GemmParams {
   float alpha_t, sigma_t, alpha_s, sigma_s;
 };
 
-enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3 };
+enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3, EPI_STAGED_F32 = 4 };
 
 template <int BM_, int BN, int EPI>
 struct GemmCfg {
@@ -137,7 +141,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles_per_z = m_tiles * n_tiles;
-  const int total_tiles = tiles_per_z * p.Z;
+  const int tiles_all_z = tiles_per_z * p.Z;
+  const int total_tiles = tiles_all_z * p.splits;   // split index is the slowest tile coordinate
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -145,10 +150,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_per_z;
-        const int t = tile - z * tiles_per_z;
+        const int split = tile / tiles_all_z;
+        const int tz = tile - split * tiles_all_z;
+        const int z = tz / tiles_per_z;
+        const int t = tz - z * tiles_per_z;
         const int mt = t / n_tiles, nt = t - mt * n_tiles;
         const int n0 = nt * BN;
+        const int kb_begin = p.splits > 1 ? split * p.kb_per_split : 0;
+        const int kb_end = p.splits > 1 ? min(p.num_kb, kb_begin + p.kb_per_split) : p.num_kb;
         // origin of each 128-row half (conv: image / row / column of its first pixel)
         int m0h[HALVES], cb[HALVES], cy[HALVES], cx[HALVES];
 #pragma unroll
@@ -169,7 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         const int bz1 = p.b_batched ? z % p.ZB1 : 0, bz2 = p.b_batched ? z / p.ZB1 : 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int tap = kb / p.kb_per_tap;
@@ -187,6 +196,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               tma_load_4d(sa + h * 16384, ma, &full_bar[stage], ka, m0h[h], z % p.ZA1, z / p.ZA1);
             }
           }
+          // stream the weight tile PF K-blocks ahead into L2 (cold weights, few CTAs: DRAM latency bound otherwise)
+          constexpr int PF = 24;
+          if (!p.b_mn_major && !p.b_batched && kb + PF < kb_end) tma_prefetch_l2_4d(&tmB, (kb + PF) * 64, n0, 0, 0);
           if (p.b_mn_major) {
             // B tile = BN/64 boxes of [64 K rows][64 N], one per 64-wide N atom
 #pragma unroll
@@ -203,9 +215,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_k = umma_idesc_f16(128, BN, false, false);
-      const uint32_t idesc_mn = umma_idesc_f16(128, BN, false, true);
-      const uint32_t idesc = p.b_mn_major ? idesc_mn : idesc_k;
+      // NOTE on issue overhead: building a 64-bit smem descriptor from an address costs ~15 dependent uniform-
+      // datapath instructions (~120 cycles) — more than the MMA itself for N <= 128 (measured: ~630 cycles per
+      // K block regardless of tile width). The descriptors are therefore formed by adding small constants to
+      // precomputed 32-bit low words; the high word (SBO, version, swizzle mode) never changes.
+      const uint32_t idesc = p.b_mn_major ? umma_idesc_f16(128, BN, false, true) : umma_idesc_f16(128, BN, false, false);
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);            // SBO=1024 B | version 1 | SW128
+      const uint32_t a_lo0 = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | (1u << 16);    // LBO field = 1 (unused, K-major)
+      const uint32_t b_lo0 = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | ((p.b_mn_major ? (8192u >> 4) : 1u) << 16);
+      const uint32_t b_kstep = p.b_mn_major ? (2048u >> 4) : 2u;                  // 16 K rows (MN-major) or 32 B
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -215,23 +233,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int split = tile / tiles_all_z;
+        const int kb_begin = p.splits > 1 ? split * p.kb_per_split : 0;
+        const int kb_end = p.splits > 1 ? min(p.num_kb, kb_begin + p.kb_per_split) : p.num_kb;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
+          const uint32_t a_lo = a_lo0 + stage * (Cfg::A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (Cfg::B_BYTES >> 4);
+          const uint32_t first = (kb > kb_begin) ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t db = p.b_mn_major ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                             : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k * b_kstep);
 #pragma unroll
             for (int h = 0; h < HALVES; ++h) {
-              const uint64_t da = umma_smem_desc(a_addr + h * 16384 + k * 32, 16, 1024);
-              umma_f16_ss(d_tmem + h * Cfg::HALF_STRIDE, da, db, idesc, (kb | k) != 0);
+              const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + h * (16384u >> 4) + k * 2u);
+              umma_f16_ss(d_tmem + h * Cfg::HALF_STRIDE, da, db, idesc, k == 0 ? first : 1u);
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb_end - 1) umma_commit(&tmem_full[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -243,8 +264,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         constexpr int units = (BN + 63) / 64;
         uint32_t runit = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-          const int z = tile / tiles_per_z;
-          const int t = tile - z * tiles_per_z;
+          const int tz = tile % tiles_all_z;
+          const int z = tz / tiles_per_z;
+          const int t = tz - z * tiles_per_z;
           const int mt = t / n_tiles, nt = t - mt * n_tiles;
           for (int half = 0; half < HALVES; ++half) {
             for (int u = 0; u < units; ++u, ++runit) {
@@ -269,7 +291,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int part = (warp - 2) >> 2;    // the two warps of a quadrant split every 64-column unit (32 columns each)
     const int row_in_tile = quad * 32 + lane;
     int iter = 0;
-    if constexpr (EPI != EPI_DIRECT) {
+    if constexpr (EPI == EPI_STAGED_F32) {
+      // ---- staged fp32 epilogue (split-K partials, fp32 row-major outputs): alpha * acc (+ bias) -> 128B-swizzled
+      // smem units of [128 rows x 32 fp32 columns], double-buffered, written out with TMA stores.
+      constexpr int units = (BN + 31) / 32;
+      const bool leader = (warp == 2 && lane == 0);
+      const uint32_t stg = smem_u32(smem_c);
+      const uint32_t sw = row_in_tile & 7;
+      uint32_t unit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int split = tile / tiles_all_z;
+        const int tz = tile - split * tiles_all_z;
+        const int z = tz / tiles_per_z;
+        const int t = tz - z * tiles_per_z;
+        const int mt = t / n_tiles, nt = t - mt * n_tiles;
+        const int acc = iter % ACC_STAGES;
+        const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int half = 0; half < HALVES; ++half) {
+          const uint32_t t_addr = tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE +
+                                  (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+          for (int u = 0; u < units; ++u, ++unit) {
+            const uint32_t buf = stg + (unit & 1) * 16384;
+            if (leader) bulk_wait_read1();
+            named_bar_sync(1, Cfg::EPI_THREADS);
+            const int col_t = u * 32 + part * 16;
+            const int ncol = nt * BN + col_t;
+            if (col_t < BN && ncol < p.N) {   // warp-uniform
+              float v[16];
+              tmem_ld16(t_addr + col_t, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr && ncol + cc * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + cc);
+                const float o0 = v[cc * 4 + 0] * p.alpha + b4.x, o1 = v[cc * 4 + 1] * p.alpha + b4.y;
+                const float o2 = v[cc * 4 + 2] * p.alpha + b4.z, o3 = v[cc * 4 + 3] * p.alpha + b4.w;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + row_in_tile * 128 +
+                                                                             (((part * 4 + cc) ^ sw) << 4)),
+                             "f"(o0), "f"(o1), "f"(o2), "f"(o3)
+                             : "memory");
+              }
+            }
+            if (u == units - 1 && half == HALVES - 1) {
+              tc_fence_before();
+              mbar_arrive(&tmem_empty[acc]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, Cfg::EPI_THREADS);
+            if (leader) {
+              const int ncol0 = nt * BN + u * 32;
+              if (u * 32 < BN && ncol0 < p.N)
+                tma_store_4d(&tmOut, smem_c + (unit & 1) * 16384, ncol0, mt * BM + half * 128, z % p.ZA1,
+                             z / p.ZA1 + split * p.split_z);
+              bulk_commit();
+            }
+          }
+        }
+      }
+      if (leader) bulk_wait0();
+    } else if constexpr (EPI != EPI_DIRECT) {
       // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual | GEGLU) -> swizzled smem -> TMA store.
       // Output is produced in 64-column units through a double-buffered staging area (2 x [128 rows x 64 cols],
       // as 32-column atoms with 64B swizzle), so the TMA store of unit u overlaps the math of unit u+1.
@@ -285,8 +369,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const bool has_res = p.res_tma != 0;
       uint32_t unit = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-        const int z = tile / tiles_per_z;
-        const int t = tile - z * tiles_per_z;
+        const int tz = tile % tiles_all_z;
+        const int z = tz / tiles_per_z;
+        const int t = tz - z * tiles_per_z;
         const int mt = t / n_tiles, nt = t - mt * n_tiles;
         const int acc = iter % ACC_STAGES;
         const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
@@ -433,14 +518,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     } else {
       // ---- direct epilogue (fp32 / transposed / unaligned outputs: conv_out, time-embedding GEMMs, N tails)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-        const int z = tile / tiles_per_z;
-        const int t = tile - z * tiles_per_z;
+        const int split = tile / tiles_all_z;
+        const int tz = tile - split * tiles_all_z;
+        const int z = tz / tiles_per_z;
+        const int t = tz - z * tiles_per_z;
         const int mt = t / n_tiles, nt = t - mt * n_tiles;
         const int acc = iter % ACC_STAGES;
         const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        const long long out_zoff = (z % p.ZA1) * p.out_z1_stride + (z / p.ZA1) * p.out_z2_stride;
+        const long long out_zoff = (z % p.ZA1) * p.out_z1_stride + (z / p.ZA1) * p.out_z2_stride +
+                                   split * p.split_out_stride;
 #pragma unroll 1
         for (int half = 0; half < HALVES; ++half) {
         const uint32_t t_addr = tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE +
@@ -474,11 +562,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             if (p.out_mode == GEMM_OUT_ROWMAJOR) {
               const long long o0 = out_zoff + static_cast<long long>(row) * p.ldc + nbase;
+              if (p.out_fp32 && nbase + 16 <= p.N &&
+                  (reinterpret_cast<uintptr_t>(reinterpret_cast<float*>(p.out) + o0) & 15) == 0) {
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o0);   // 64 B per thread
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (nbase + j < p.N) {
-                  if (p.out_fp32) reinterpret_cast<float*>(p.out)[o0 + j] = v[j];
-                  else reinterpret_cast<__half*>(p.out)[o0 + j] = __float2half_rn(v[j]);
+                for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (nbase + j < p.N) {
+                    if (p.out_fp32) reinterpret_cast<float*>(p.out)[o0 + j] = v[j];
+                    else reinterpret_cast<__half*>(p.out)[o0 + j] = __float2half_rn(v[j]);
+                  }
                 }
               }
             } else {

@@ -49,10 +49,26 @@ def _f16(t, name):
         raise ValueError(f"{name}: expected a CUDA fp16 tensor, got {t.dtype} on {t.device}")
 
 
+_splitk_ws = {}
+SPLITK_WS_BYTES = 64 << 20
+
+
+def _workspace(device):
+    """fp32 split-K scratch (one per device, stream-ordered reuse). Allocated on first use — i.e. during the eager
+    warm-up, never inside a CUDA-graph capture."""
+    key = str(device)
+    if key not in _splitk_ws:
+        _splitk_ws[key] = torch.empty(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
+    return _splitk_ws[key]
+
+
 def gemm_raw(**kw):
     """Fill an IcdGemm from keyword fields (tensors are converted to device pointers) and launch."""
     g = _lib.IcdGemm()
     g.alpha = 1.0
+    if "ws" not in kw and isinstance(kw.get("out"), torch.Tensor):
+        ws = _workspace(kw["out"].device)
+        kw["ws"], kw["ws_bytes"] = ws, ws.numel() * 4
     for k, v in kw.items():
         if isinstance(v, torch.Tensor):
             v = v.data_ptr()
@@ -75,7 +91,7 @@ def pick_bn(M, N, Z=1, geglu=False, b_mn_major=False, force_bn=0):
 
 
 def linear(a, w, bias=None, out=None, residual=None, a1=None, rowvec=None, rows_per_img=0, geglu=False,
-           out_fp32=False, alpha=1.0, force_bn=0, force_bm=0):
+           out_fp32=False, alpha=1.0, force_bn=0, force_bm=0, force_splits=0):
     """out[M, N] = epilogue(alpha * [a | a1] @ w.T).  a: [M, K0] (row stride allowed), w: [N, K0+K1]."""
     _f16(a, "a"); _f16(w, "w")
     M, K0 = a.shape
@@ -89,12 +105,12 @@ def linear(a, w, bias=None, out=None, residual=None, a1=None, rowvec=None, rows_
              rows_per_img=rows_per_img, ldv=rowvec.stride(0) if rowvec is not None else 0, residual=residual,
              ldr=residual.stride(0) if residual is not None else 0, out=out, ldc=out.stride(0),
              out_fp32=int(out.dtype == torch.float32), out_mode=0, geglu=int(geglu), force_bn=force_bn,
-             force_bm=force_bm)
+             force_bm=force_bm, force_splits=force_splits)
     return out
 
 
 def conv3x3(x0, w, B, H, W, bias=None, x1=None, rowvec=None, residual=None, out=None, out_fp32=False,
-            nchw_out=None, upd_x=None, upd_out=None, upd_coefs=None, force_bn=0, force_bm=0):
+            nchw_out=None, upd_x=None, upd_out=None, upd_coefs=None, force_bn=0, force_bm=0, force_splits=0):
     """3x3 / pad 1 / stride 1 convolution as implicit GEMM.
     x0: [B*H*W, C0] (NHWC), optional x1: [B*H*W, C1] concatenated along channels; w: [Cout, 9*(C0+C1)] packed
     (ky, kx, cin). `nchw_out`: fp32 [B, Cout, H, W] transposed store (conv_out); with upd_* the consistency
@@ -108,7 +124,7 @@ def conv3x3(x0, w, B, H, W, bias=None, x1=None, rowvec=None, residual=None, out=
               B=B, H=H, W=W, b=w, b_ld=w.stride(0), ZB1=1, M=M, N=N, K=C0 + C1, Z=1, alpha=1.0, bias=bias,
               rowvec=rowvec, rows_per_img=H * W, ldv=rowvec.stride(0) if rowvec is not None else 0,
               residual=residual, ldr=residual.stride(0) if residual is not None else 0, force_bn=force_bn,
-              force_bm=force_bm)
+              force_bm=force_bm, force_splits=force_splits)
     if nchw_out is not None:
         kw.update(out=nchw_out, ldc=H * W, out_imgstride=N * H * W, out_fp32=1, out_mode=1)
         if upd_x is not None:

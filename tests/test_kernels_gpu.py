@@ -57,6 +57,24 @@ def test_linear_256row_tiles(ops, M, K, N, bn):
     _close(out32, a.float() @ w.float().t() + bias, rtol=1e-4, atol=1e-3, what="bm256 fp32")
 
 
+@pytest.mark.parametrize("splits,bm", [(3, 0), (4, 256), (0, 0)])
+def test_split_k(ops, splits, bm):
+    """Few-tile, deep-K problems (the 8x8-level convs): K split over CTAs, fp32 partials + fused reduce epilogue."""
+    from invertible_cd_b200.packing import pack_conv3x3
+    B, H, W, Cin, Cout = 8, 8, 8, 320, 1280
+    x = _rand(B * H * W, Cin, seed=70)
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=71)
+    bias, rv = torch.randn(Cout, device="cuda"), torch.randn(B, Cout, device="cuda")
+    res = _rand(B * H * W, Cout, seed=72)
+    out = ops.conv3x3(x, pack_conv3x3(w), B, H, W, bias=bias, rowvec=rv, residual=res, force_splits=splits,
+                      force_bm=bm)
+    ref = _conv_ref(x, w, B, H, W, bias) + rv.repeat_interleave(H * W, 0) + res.float()
+    _close(out, ref, what=f"split-K conv splits={splits}")
+    a, wl = _rand(300, 4096, seed=73), _rand(320, 4096, scale=1 / 64, seed=74)
+    o2 = ops.linear(a, wl, bias=torch.ones(320, device="cuda"), force_splits=splits or 2, alpha=0.5)
+    _close(o2, 0.5 * (a.float() @ wl.float().t()) + 1.0, what="split-K linear")
+
+
 def test_linear_fp32_out_and_alpha(ops):
     a, w = _rand(200, 192, seed=4), _rand(96, 192, scale=0.1, seed=5)
     out = ops.linear(a, w, out_fp32=True, alpha=0.25)
