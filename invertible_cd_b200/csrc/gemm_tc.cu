@@ -125,7 +125,10 @@ static TileChoice pick_tile(int M, int N, int Z, int num_kb, int geglu, int b_mn
         if (bn > 64 && N <= bn / 2) continue;  // mostly-empty tile
       }
       const long long tiles = static_cast<long long>((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Z;
-      const double mma = bm * bn / 64.0;               // cycles per 64-deep K block
+      // 4 K-steps per block; back-to-back MMAs into the SAME accumulator are latency-chained (~157 cycles each,
+      // measured), so a 128-row tile never beats ~630 cycles per K block; 256-row tiles interleave two chains
+      const double chain = 157.0 / (bm / 128);
+      const double mma = 4.0 * (bm / 128) * ((bn / 2.0) > chain ? (bn / 2.0) : chain);
       const double l2 = 3.0 * (bm + bn);               // (bm+bn) * 128 B / ~42.5 B/clk/SM
       const double epi = (bm / 128) * (600.0 + 6.0 * bn) * (geglu ? 3.0 : 1.0);
       const int half_stride = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
@@ -160,7 +163,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  const long long tiles = static_cast<long long>((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.Z;
+  const long long tiles = static_cast<long long>((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.Z * p.splits;
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
   gemm_tc_kernel<BM, BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, o, r, p);
@@ -232,7 +235,7 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   if (g->M <= 0 || g->N <= 0 || g->Z <= 0) return set_error("icd_gemm: empty problem");
   const int kb_est = ((g->K0 + 63) / 64 + (g->a1 != nullptr ? (g->K1 + 63) / 64 : 0)) * (g->a_mode == 1 ? 9 : 1);
   // small-K GEMMs with a residual use the TMA-streamed residual variant, which exists for 128-row tiles only
-  const int fbm = (g->force_bm == 0 && g->residual != nullptr && kb_est <= 24) ? 128 : g->force_bm;
+  const int fbm = g->force_bm;
   // split-K (fp32 partials in the caller's workspace + a reduce kernel) for few-tile, deep-K problems
   const bool split_ok = g->ws != nullptr && !g->geglu && !g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR &&
                         g->Z == 1 && (g->N % 16) == 0 && g->upd_x == nullptr && (g->ldc % 8) == 0 &&
@@ -244,7 +247,6 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     if (max_splits > 16) max_splits = 16;
     if (max_splits < 1) max_splits = 1;
   }
-  max_splits = 1;   // measured (tools/splitk_probe.py): no gain yet on B200 for the 8x8-level shapes -> opt-in only
   TileChoice tc = pick_tile(g->M, g->N, g->Z, kb_est, g->geglu, g->b_mn_major, g->force_bn, fbm, max_splits);
   if (g->force_splits > 0) {
     tc = pick_tile(g->M, g->N, g->Z, kb_est, g->geglu, g->b_mn_major, g->force_bn, fbm, 1);
@@ -452,7 +454,12 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     return set_error("icd_gemm: GEGLU supports BN 128 / 256");
   }
   // short main loops cannot hide the row-per-thread residual reads: stream the residual through TMA + smem
-  if (p.epi_tma && p.res_tma && p.num_kb <= 24 && bm == 128) { ICD_LAUNCH_BN(128, EPI_STAGED_RES) }
+  if (p.epi_tma && p.res_tma && p.num_kb <= 24) {
+    if (bm == 128) { ICD_LAUNCH_BN(128, EPI_STAGED_RES) }
+    if (bn == 64) ICD_LAUNCH(256, 64, EPI_STAGED_RES);
+    if (bn == 128) ICD_LAUNCH(256, 128, EPI_STAGED_RES);
+    if (bn == 160) ICD_LAUNCH(256, 160, EPI_STAGED_RES);
+  }
   if (p.epi_tma) {
     if (bm == 256) { ICD_LAUNCH_BN(256, EPI_STAGED) }
     ICD_LAUNCH_BN(128, EPI_STAGED)
