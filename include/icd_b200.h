@@ -29,6 +29,12 @@ const char* icd_last_error(void);
 /* library / device probe: returns 0 and fills sm_count, cc_major, cc_minor */
 int icd_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int icd_abi_version(void);
+/* Programmatic dependent launch (every kernel of the library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and calls griddepcontrol.wait before its first global-memory
+ * access, so consecutive kernels overlap prologue with tail — eagerly and inside captured CUDA graphs).
+ * Default on (env ICD_PDL=0 disables); returns the previous setting. No reference counterpart: the reference's
+ * eager PyTorch launches (utils/generation.py:241) are fully serialised. */
+int icd_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05 tensor cores:  D = epilogue(alpha * A . B^T), fp32 accumulation.

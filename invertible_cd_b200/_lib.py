@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libicd_b200.so")
 
 # every symbol include/icd_b200.h declares (tests assert the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "icd_last_error", "icd_device_info", "icd_abi_version", "icd_gemm", "icd_gemm_pick_bn", "icd_attention",
+    "icd_last_error", "icd_device_info", "icd_abi_version", "icd_set_pdl", "icd_gemm", "icd_gemm_pick_bn", "icd_attention",
     "icd_groupnorm", "icd_layernorm", "icd_softmax", "icd_upsample2x", "icd_im2col_s2", "icd_latent_to_nhwc",
     "icd_timestep_embedding", "icd_guidance_embedding", "icd_silu", "icd_add", "icd_consistency_update",
 ]
@@ -52,6 +52,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.icd_last_error.restype = C.c_char_p
     lib.icd_abi_version.restype = C.c_int
+    lib.icd_set_pdl.argtypes = [C.c_int]
     lib.icd_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     lib.icd_gemm.argtypes = [C.POINTER(IcdGemm), C.c_void_p]
     lib.icd_gemm_pick_bn.argtypes = [C.c_int] * 6

@@ -87,6 +87,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q0 = qt * 128;
   const int n_kv = (p.Nk + BKV - 1) / BKV;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -113,6 +114,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // prologue above overlaps the previous kernel's tail; Q/K/V are read below
   const uint32_t tmem_O = tmem_base + 128;
   const uint32_t tmem_L = tmem_O + DP;       // row sums: L = P . 1 accumulated by the tensor core
 
@@ -286,16 +288,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld_wait();
       inv = 1.f / l16[0];
     }
-    if (p.probs != nullptr && n_kv <= 2 && q < p.Nq) {
-      // <= 128 keys: both P tiles are still in smem -> emit the normalised probabilities (AttentionStore capture)
-      __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
-      for (int c = 0; c < p.Nk; ++c) {
-        const int t = c >> 6, cc = c & 63;
-        const uint32_t addr = p_row + t * 16384 + (((cc >> 3) ^ sw) << 4) + (cc & 7) * 2;
-        unsigned short u;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
-        const float sc = (t == 0 && n_kv == 2) ? inv * alpha_after0 : inv;
-        pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * sc);
+    if (p.probs != nullptr && n_kv <= 2) {
+      // <= 128 keys: both P tiles are still in smem -> emit the normalised probabilities (AttentionStore capture).
+      // Each warp owns 32 consecutive rows whose P was written by its own lanes, so a warp-level sync suffices.
+      const float sc0 = (n_kv == 2) ? inv * alpha_after0 : inv;   // tile 0 was written before the last rescale
+      __syncwarp();
+      if ((p.probs_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(p.probs) & 15) == 0) {
+        // coalesced: consecutive lanes write consecutive 16-byte chunks; the whole padded row [0, probs_ld) is
+        // written (masked keys have P == 0, chunks beyond the last tile are zero-filled)
+        const int nchunk = static_cast<int>(p.probs_ld >> 3);
+        const int row0 = quad * 32;
+        uint4* dst = reinterpret_cast<uint4*>(p.probs + (static_cast<long long>(bh) * p.Nq + q0 + row0) * p.probs_ld);
+        const int rows_valid = p.Nq - (q0 + row0);
+        for (int idx = lane; idx < 32 * nchunk; idx += 32) {
+          const int r = idx / nchunk, ch = idx - r * nchunk;
+          const float s0 = __shfl_sync(0xffffffffu, sc0, r), s1 = __shfl_sync(0xffffffffu, inv, r);
+          const int t = ch >> 3, cc = ch & 7;
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (t < n_kv) {
+            const int rr = row0 + r;
+            const uint32_t addr = smem_u32(sP) + rr * 128 + t * 16384 + ((cc ^ (rr & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(addr));
+            const float sc = t == 0 ? s0 : s1;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&val);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+              const __half2 h2 = __floats2half2_rn(f.x * sc, f.y * sc);
+              w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+          }
+          if (r < rows_valid) dst[idx] = val;
+        }
+      } else if (q < p.Nq) {
+        __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
+        for (int c = 0; c < p.Nk; ++c) {
+          const int t = c >> 6, cc = c & 63;
+          const uint32_t addr = p_row + t * 16384 + (((cc >> 3) ^ sw) << 4) + (cc & 7) * 2;
+          unsigned short u;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
+          pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * (t == 0 ? sc0 : inv));
+        }
       }
     }
     __half* orow = p.out + (static_cast<long long>(b) * p.Nq + q) * p.out_ld + h * D;
@@ -342,7 +377,7 @@ static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const 
     configured = true;
   }
   const int grid = p.B * p.H * ((p.Nq + 127) / 128);
-  attention_tc_kernel<D><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  launch_k(attention_tc_kernel<D>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, tq, tk, tv, p);
   return check_launch("attention_tc");
 }
 

@@ -10,6 +10,8 @@ namespace icd {
 // y[b][2h+dy][2w+dx][:] = x[b][h][w][:]   (Upsample2D: F.interpolate(scale_factor=2, mode="nearest"))
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B,
                                                          int H, int W, int vpc /*vectors per pixel*/) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * H * W * vpc;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -32,6 +34,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
 // y[(b,ho,wo)][tap][c] = x[b][2ho+ky-1][2wo+kx-1][c] (zero outside): operand of the stride-2 Downsample2D conv
 __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H,
                                                         int W, int vpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * 9 * vpc;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -54,6 +58,8 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4* __restrict_
 // NCHW fp32 -> NHWC fp16, channels zero-padded to Cpad
 __global__ void __launch_bounds__(256) latent_to_nhwc_kernel(const float* __restrict__ x, __half* __restrict__ y, int B,
                                                              int C, int HW, int Cpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * HW;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -70,6 +76,8 @@ __global__ void __launch_bounds__(256) latent_to_nhwc_kernel(const float* __rest
 // with the reference's fp32 op order so the arguments are bit-identical.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
                                           __half* __restrict__ y, int n, int half_dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half_dim) return;
   const int r = i / half_dim, k = i - r * half_dim;
@@ -81,6 +89,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, const flo
 // guidance_scale_embedding (utils/generation.py:96-122): emb = (1000 w) * f_i ; y = [sin | cos]
 __global__ void guidance_embedding_kernel(const float* __restrict__ w, const float* __restrict__ freqs,
                                           __half* __restrict__ y, int n, int half_dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half_dim) return;
   const int r = i / half_dim, k = i - r * half_dim;
@@ -90,6 +100,8 @@ __global__ void guidance_embedding_kernel(const float* __restrict__ w, const flo
 }
 
 __global__ void __launch_bounds__(256) silu_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float v = __half2float(x[i]);
@@ -99,6 +111,8 @@ __global__ void __launch_bounds__(256) silu_kernel(const __half* __restrict__ x,
 
 __global__ void __launch_bounds__(256) add_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
                                                   __half* __restrict__ y, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = __float2half_rn(__half2float(a[i]) + __half2float(b[i]));
@@ -110,6 +124,8 @@ consistency_update_kernel(const float* __restrict__ eps, const float* __restrict
                           long long per_sample, int B, const float* __restrict__ alpha_t,
                           const float* __restrict__ sigma_t, const float* __restrict__ alpha_s,
                           const float* __restrict__ sigma_s) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = per_sample * B;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -135,8 +151,7 @@ using namespace icd;
 extern "C" int icd_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stream) {
   if (C % 8 != 0) return set_error("icd_upsample2x: C must be a multiple of 8");
   const int vpc = C / 8;
-  upsample2x_kernel<<<grid_for(static_cast<long long>(B) * H * W * vpc), 256, 0,
-                      reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(x),
+  launch_k(upsample2x_kernel, dim3(grid_for(static_cast<long long>(B) * H * W * vpc)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint4*>(x),
                                                                 reinterpret_cast<uint4*>(y), B, H, W, vpc);
   return check_launch("upsample2x");
 }
@@ -144,14 +159,13 @@ extern "C" int icd_upsample2x(const void* x, void* y, int B, int H, int W, int C
 extern "C" int icd_im2col_s2(const void* x, void* y, int B, int H, int W, int C, void* stream) {
   if (C % 8 != 0 || (H & 1) || (W & 1)) return set_error("icd_im2col_s2: C % 8 != 0 or odd H/W");
   const int vpc = C / 8;
-  im2col_s2_kernel<<<grid_for(static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * vpc), 256, 0,
-                     reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(x),
+  launch_k(im2col_s2_kernel, dim3(grid_for(static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * vpc)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint4*>(x),
                                                                reinterpret_cast<uint4*>(y), B, H, W, vpc);
   return check_launch("im2col_s2");
 }
 
 extern "C" int icd_latent_to_nhwc(const float* x, void* y, int B, int C, int HW, int Cpad, void* stream) {
-  latent_to_nhwc_kernel<<<grid_for(static_cast<long long>(B) * HW), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(latent_to_nhwc_kernel, dim3(grid_for(static_cast<long long>(B) * HW)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__half*>(y), B, C, HW, Cpad);
   return check_launch("latent_to_nhwc");
 }
@@ -159,7 +173,7 @@ extern "C" int icd_latent_to_nhwc(const float* x, void* y, int B, int C, int HW,
 extern "C" int icd_timestep_embedding(const float* t, const float* freqs, void* y, int n, int dim, void* stream) {
   if (dim & 1) return set_error("icd_timestep_embedding: odd dim");
   const int total = n * (dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       t, freqs, reinterpret_cast<__half*>(y), n, dim / 2);
   return check_launch("timestep_embedding");
 }
@@ -167,19 +181,19 @@ extern "C" int icd_timestep_embedding(const float* t, const float* freqs, void* 
 extern "C" int icd_guidance_embedding(const float* w, const float* freqs, void* y, int n, int dim, void* stream) {
   if (dim & 1) return set_error("icd_guidance_embedding: odd dim");
   const int total = n * (dim / 2);
-  guidance_embedding_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(guidance_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       w, freqs, reinterpret_cast<__half*>(y), n, dim / 2);
   return check_launch("guidance_embedding");
 }
 
 extern "C" int icd_silu(const void* x, void* y, long long n, void* stream) {
-  silu_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __half*>(x),
+  launch_k(silu_kernel, dim3(grid_for(n)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __half*>(x),
                                                                               reinterpret_cast<__half*>(y), n);
   return check_launch("silu");
 }
 
 extern "C" int icd_add(const void* a, const void* b, void* y, long long n, void* stream) {
-  add_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(add_kernel, dim3(grid_for(n)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(a), reinterpret_cast<const __half*>(b), reinterpret_cast<__half*>(y), n);
   return check_launch("add");
 }
@@ -187,7 +201,7 @@ extern "C" int icd_add(const void* a, const void* b, void* y, long long n, void*
 extern "C" int icd_consistency_update(const float* eps, const float* x, float* out, long long per_sample, int B,
                                       const float* alpha_t, const float* sigma_t, const float* alpha_s,
                                       const float* sigma_s, void* stream) {
-  consistency_update_kernel<<<grid_for(per_sample * B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(consistency_update_kernel, dim3(grid_for(per_sample * B)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       eps, x, out, per_sample, B, alpha_t, sigma_t, alpha_s, sigma_s);
   return check_launch("consistency_update");
 }

@@ -166,7 +166,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   const long long tiles = static_cast<long long>((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.Z * p.splits;
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BM, BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, o, r, p);
+  launch_k(gemm_tc_kernel<BM, BN, EPI>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, a0, a1, b, o, r, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return 0;
@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float alpha, const float* __restrict__ bias,
                      const float* __restrict__ rowvec, int rows_per_img, int ldv, const __half* __restrict__ res,
                      long long ldr, __half* __restrict__ out, long long ldc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nv = N >> 3;
   const long long total = static_cast<long long>(M) * nv;
   const long long mn = static_cast<long long>(M) * N;
@@ -216,7 +218,7 @@ static int launch_splitk_reduce(const float* ws, int splits, int M, int N, float
   long long grid = (total + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (grid > cap) grid = cap;
-  splitk_reduce_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(ws, splits, M, N, alpha, bias, rowvec,
+  launch_k(splitk_reduce_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, st, ws, splits, M, N, alpha, bias, rowvec,
                                                                     rows_per_img, ldv, res, ldr, out, ldc);
   return check_launch("splitk_reduce");
 }

@@ -1,5 +1,7 @@
 #include "host_util.h"
 
+#include <cstdlib>
+
 #include "../../include/icd_b200.h"
 
 namespace icd {
@@ -22,6 +24,14 @@ int sm_count() {
   }
   return n;
 }
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("ICD_PDL");
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string(what) + ": " + cudaGetErrorString(e));
@@ -31,6 +41,11 @@ int check_launch(const char* what) {
 
 extern "C" const char* icd_last_error(void) { return icd::g_err.c_str(); }
 extern "C" int icd_abi_version(void) { return 1; }
+extern "C" int icd_set_pdl(int enabled) {
+  const int prev = icd::pdl_enabled() ? 1 : 0;
+  icd::g_pdl = enabled ? 1 : 0;
+  return prev;
+}
 extern "C" int icd_device_info(int* sms, int* major, int* minor) {
   int dev = 0;
   cudaDeviceProp prop;

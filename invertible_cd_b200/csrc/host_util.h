@@ -8,4 +8,24 @@ namespace icd {
 int set_error(const std::string& msg);  // records the message, returns 1
 int sm_count();                          // SMs of the current device (148 on B200); 148 if no device is visible
 int check_launch(const char* what);      // cudaGetLastError -> set_error
+bool pdl_enabled();                      // programmatic dependent launch (ICD_PDL=0 or icd_set_pdl(0) disables)
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start (up to its pdl_wait()) before
+// its predecessor in the stream has finished. Every kernel launched through this calls pdl_wait() before touching
+// global memory. Works under stream capture (becomes a programmatic edge of the CUDA graph).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace icd

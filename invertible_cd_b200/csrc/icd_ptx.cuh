@@ -12,6 +12,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (host_util.h):
+// the next kernel of the stream / graph may become resident while this one is still running and executes its
+// prologue (barrier init, TMEM allocation, descriptor prefetch) under this kernel's tail. pdl_wait() blocks until
+// every prerequisite grid has COMPLETED and its memory is visible: it must precede the first global-memory access.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

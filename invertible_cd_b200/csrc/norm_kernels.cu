@@ -25,6 +25,8 @@ __device__ __forceinline__ const __half* gn_vec_ptr(const GnSrc& s, long long pi
 
 // partial sums: ws[((b * chunks + chunk) * 2 + {0:sum,1:sumsq}) * 32 + g]
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW, int cpg, int chunks, float* ws) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = src.C0 + src.C1;
   const int vpr = C >> 3;                      // 16-byte vectors per pixel
   const int rows_per_iter = GN_THREADS / vpr;  // >= 1 (C <= 2560)
@@ -118,19 +120,31 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
   const int rows_per_iter = GN_THREADS / vpr;
   const int b = blockIdx.y, chunk = blockIdx.x;
   __shared__ float s_mean[32], s_rstd[32];
-  if (threadIdx.x < 32) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x < 256) {
+    // finalize the statistics: 8 lanes per group sum the per-chunk partials (strided, fixed order) in fp64, then a
+    // 3-step shuffle tree combines them — deterministic, and ~10x shorter than one thread walking all chunks
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
     double s = 0.0, q = 0.0;
     const float* w = ws + static_cast<long long>(b) * chunks * 64;
-    for (int i = 0; i < chunks; ++i) {
-      s += static_cast<double>(w[i * 64 + threadIdx.x]);
-      q += static_cast<double>(w[i * 64 + 32 + threadIdx.x]);
+    for (int i = l; i < chunks; i += 8) {
+      s += static_cast<double>(w[i * 64 + g]);
+      q += static_cast<double>(w[i * 64 + 32 + g]);
     }
-    const double n = static_cast<double>(HW) * cpg;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (l == 0) {
+      const double n = static_cast<double>(HW) * cpg;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
   }
   __syncthreads();
   const int v = threadIdx.x % vpr, r = threadIdx.x / vpr;
@@ -182,6 +196,8 @@ template <int MAXV>  // max 16-byte vectors per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows,
                                                         int C, float eps, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -242,6 +258,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 
 // one warp per row, in place; three passes (row is L1/L2 resident)
 __global__ void __launch_bounds__(256) softmax_kernel(__half* __restrict__ x, long long rows, int cols, long long ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -275,15 +293,17 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   GnSrc src{reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), C0, x1 != nullptr ? C1 : 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int chunks = (4 * sm_count() + B - 1) / B;
+  { const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS); if (chunks > max_by_rows) chunks = max_by_rows; }
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
   if (chunks > HW) chunks = HW;
   if (chunks < 1) chunks = 1;
-  gn_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, st>>>(src, HW, cpg, chunks, stats_ws);
+  launch_k(gn_stats_kernel, dim3(chunks, B), dim3(GN_THREADS), 0, st, src, HW, cpg, chunks, stats_ws);
   if (check_launch("gn_stats")) return 1;
-  int apply_chunks = (6 * sm_count() + B - 1) / B;
+  int apply_chunks = (4 * sm_count() + B - 1) / B;
+  { const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS); if (apply_chunks > max_by_rows) apply_chunks = max_by_rows; }
   if (apply_chunks > HW) apply_chunks = HW;
   if (apply_chunks < 1) apply_chunks = 1;
-  gn_apply_kernel<<<dim3(apply_chunks, B), GN_THREADS, 0, st>>>(src, reinterpret_cast<__half*>(y), HW, cpg, chunks,
+  launch_k(gn_apply_kernel, dim3(apply_chunks, B), dim3(GN_THREADS), 0, st, src, reinterpret_cast<__half*>(y), HW, cpg, chunks,
                                                                 apply_chunks, eps, gamma, beta, apply_silu, stats_ws);
   return check_launch("gn_apply");
 }
@@ -298,11 +318,11 @@ extern "C" int icd_layernorm(const void* x, void* y, int rows, int C, float eps,
   const __half* xp = reinterpret_cast<const __half*>(x);
   __half* yp = reinterpret_cast<__half*>(y);
   if (nvec <= 64)
-    layernorm_kernel<2><<<grid, 256, 0, st>>>(xp, yp, rows, C, eps, gamma, beta);
+    launch_k(layernorm_kernel<2>, dim3(grid), dim3(256), 0, st, xp, yp, rows, C, eps, gamma, beta);
   else if (nvec <= 160)
-    layernorm_kernel<5><<<grid, 256, 0, st>>>(xp, yp, rows, C, eps, gamma, beta);
+    launch_k(layernorm_kernel<5>, dim3(grid), dim3(256), 0, st, xp, yp, rows, C, eps, gamma, beta);
   else if (nvec <= 320)
-    layernorm_kernel<10><<<grid, 256, 0, st>>>(xp, yp, rows, C, eps, gamma, beta);
+    launch_k(layernorm_kernel<10>, dim3(grid), dim3(256), 0, st, xp, yp, rows, C, eps, gamma, beta);
   else
     return set_error("icd_layernorm: C > 2560 unsupported");
   return check_launch("layernorm");
@@ -311,6 +331,6 @@ extern "C" int icd_layernorm(const void* x, void* y, int rows, int C, float eps,
 extern "C" int icd_softmax(void* x, long long rows, int cols, long long ld, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long grid = (rows + 7) / 8;
-  softmax_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(reinterpret_cast<__half*>(x), rows, cols, ld);
+  launch_k(softmax_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, st, reinterpret_cast<__half*>(x), rows, cols, ld);
   return check_launch("softmax");
 }

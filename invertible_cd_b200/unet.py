@@ -253,7 +253,8 @@ class B200UNet:
             return out
         ldp = (Nk + 7) // 8 * 8
         if req == "read" and Nk <= 128:
-            probs = torch.zeros((B * heads, Nq, ldp), device=q.device, dtype=torch.float16)
+            # the kernel writes every padded row completely (pad columns are zero): no memset needed
+            probs = torch.empty((B * heads, Nq, ldp), device=q.device, dtype=torch.float16)
             out = ops.attention(q, k, v, B, heads, Nq, Nk, d, scale, probs_out=probs)
             ctrl.call_rows(probs[..., :Nk], is_cross, place, self._cond_only)
             return out

@@ -335,9 +335,28 @@ def test_attention_fused_cross_with_capture(ops, B, H, Nq, D):
     kv = _rand(B * Nk, 2 * H * D, seed=64)          # K and V as column slices of one projection output
     k, v = kv[:, :H * D], kv[:, H * D:]
     scale = D ** -0.5
-    probs = torch.zeros(B * H, Nq, 80, device="cuda", dtype=torch.float16)
+    # garbage-initialised capture buffer: the kernel must write every padded row completely (pad columns = 0)
+    probs = torch.full((B * H, Nq, 80), float("nan"), device="cuda", dtype=torch.float16)
     out = ops.attention(q, k, v, B, H, Nq, Nk, D, scale, probs_out=probs)
     ref_o, ref_p = _attn_ref(q, k, v, B, H, Nq, Nk, D, scale)
     _close(out, ref_o, rtol=2e-3, atol=2e-3, what="fused cross out")
     _close(probs[..., :Nk], ref_p, rtol=2e-3, atol=2e-4, what="fused cross probs")
     assert probs[..., Nk:].abs().max() == 0
+
+
+@pytest.mark.parametrize("Nq,Nk,ldp", [(200, 64, 64), (200, 128, 128), (77, 100, 104), (130, 13, 16), (96, 77, 77),
+                                       (300, 77, 144)])
+def test_attention_capture_ragged(ops, Nq, Nk, ldp):
+    """Capture write-out on ragged shapes: partial query tiles, 1 and 2 key tiles, padded / over-wide / unaligned
+    (scalar fallback) row strides. Large scores force the lazy rescale between the two key tiles."""
+    B, H, D = 2, 3, 40
+    q = _rand(B * Nq, H * D, seed=70) * 4
+    k, v = _rand(B * Nk, H * D, seed=71) * 4, _rand(B * Nk, H * D, seed=72)
+    scale = D ** -0.5
+    probs = torch.zeros((B * H, Nq, ldp), device="cuda", dtype=torch.float16)
+    out = ops.attention(q, k, v, B, H, Nq, Nk, D, scale, probs_out=probs)
+    ref_o, ref_p = _attn_ref(q, k, v, B, H, Nq, Nk, D, scale)
+    _close(out, ref_o, rtol=2e-3, atol=2e-3, what="ragged capture out")
+    _close(probs[..., :Nk], ref_p, rtol=3e-3, atol=3e-4, what="ragged capture probs")
+    if ldp > Nk:
+        assert probs[..., Nk:].abs().max() == 0

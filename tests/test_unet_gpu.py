@@ -179,3 +179,43 @@ def test_edit_controller_matches_oracle():
     print("edit:", emax, el2)
     assert el2 <= 6e-3, (emax, el2)
     assert ctrl.cur_step == 1 and ref_ctrl.cur_step == 1
+
+
+def test_pdl_on_off_bit_identical_eager_and_graph():
+    """Programmatic dependent launch only overlaps each kernel's prologue with its predecessor's tail: results must be
+    bit-identical with it on or off, eagerly and when the whole forward is replayed from a captured CUDA graph."""
+    from invertible_cd_b200 import _lib
+    from invertible_cd_b200.unet import B200UNet
+    acfg, oracle = _mk("small_sd15")
+    lat, ctx, w, _ = _inputs(acfg, 2)
+    unet = B200UNet(acfg, dict(oracle.state_dict()), "cuda")
+    lat, ctx, w, t = lat.cuda(), ctx.cuda(), w.cuda(), torch.tensor(519)
+    lib = _lib.load()
+
+    def fwd():
+        return unet(lat, t, encoder_hidden_states=ctx, timestep_cond=w)["sample"]
+
+    prev = lib.icd_set_pdl(0)
+    try:
+        ref = fwd().clone()
+        lib.icd_set_pdl(1)
+        for _ in range(3):
+            got = fwd()
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            gout = fwd()
+        for _ in range(3):
+            gout.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(gout, ref)
+    finally:
+        lib.icd_set_pdl(prev)
