@@ -119,7 +119,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_L = tmem_O + DP;       // row sums: L = P . 1 accumulated by the tensor core
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int a = 0; a < DATOMS; ++a) tma_load_4d(sQ + a * 16384, &tmQ, q_full, a * 64, h, q0, b);
@@ -139,7 +139,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, BKV, false, false);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, DP, false, true);
       constexpr uint32_t idesc_l = umma_idesc_f16(128, 16, false, false);

@@ -148,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -216,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       // NOTE on issue overhead: building a 64-bit smem descriptor from an address costs ~15 dependent uniform-
       // datapath instructions (~120 cycles) — more than the MMA itself for N <= 128 (measured: ~630 cycles per
       // K block regardless of tile width). The descriptors are therefore formed by adding small constants to
@@ -262,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == 10) {
     // ------------------------------------------------------------------ residual producer (EPI_STAGED_RES only)
     if constexpr (EPI == EPI_STAGED_RES) {
-      if (lane == 0) {
+      if (elect_one()) {
         constexpr int units = (BN + 63) / 64;
         uint32_t runit = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -297,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // ---- staged fp32 epilogue (split-K partials, fp32 row-major outputs): alpha * acc (+ bias) -> 128B-swizzled
       // smem units of [128 rows x 32 fp32 columns], double-buffered, written out with TMA stores.
       constexpr int units = (BN + 31) / 32;
-      const bool leader = (warp == 2 && lane == 0);
+      const bool leader = (warp == 2) && elect_one();
       const uint32_t stg = smem_u32(smem_c);
       const uint32_t sw = row_in_tile & 7;
       uint32_t unit = 0;
@@ -365,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       constexpr int outw = GEGLU ? BN / 2 : BN;   // output columns per tile
       constexpr int units = (outw + 63) / 64;
       const int n_out_total = GEGLU ? p.N / 2 : p.N;
-      const bool leader = (warp == 2 && lane == 0);
+      const bool leader = (warp == 2) && elect_one();
       const uint32_t stg = smem_u32(smem_c);
       const uint32_t sw = (row_in_tile >> 1) & 3; // 64B swizzle: 16B-chunk index ^= (row / 2) % 4
       const bool has_res = p.res_tma != 0;

@@ -20,6 +20,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------- single-thread election
+// `if (elect_one())` instead of `if (lane == 0)`: ptxas recognises elect.sync and knows exactly one lane runs the
+// guarded code, so operands of UTCHMMA / UTMALDG / UTCBAR (tcgen05.mma, TMA, tcgen05.commit) move to uniform
+// registers directly. Behind a plain `lane == 0` test every such instruction is wrapped in an ELECT / BRA.U.ANY
+// "waterfall" loop (~100+ issue cycles per MMA: measured 138 cycles per tcgen05.mma regardless of N).
+// The warp must be converged when calling.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

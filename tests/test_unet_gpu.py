@@ -189,7 +189,7 @@ def test_pdl_on_off_bit_identical_eager_and_graph():
     acfg, oracle = _mk("small_sd15")
     lat, ctx, w, _ = _inputs(acfg, 2)
     unet = B200UNet(acfg, dict(oracle.state_dict()), "cuda")
-    lat, ctx, w, t = lat.cuda(), ctx.cuda(), w.cuda(), torch.tensor(519)
+    lat, ctx, w, t = lat.cuda(), ctx.cuda(), w.cuda(), 519   # python int: no H2D copy inside the capture
     lib = _lib.load()
 
     def fwd():

@@ -8,8 +8,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from invertible_cd_b200 import ops  # noqa: E402
+from tools._timing import time_us  # noqa: E402
 
 SHAPES = [(8, 8, 4096, 4096, 40), (8, 8, 1024, 1024, 80), (8, 8, 256, 256, 160), (8, 8, 4096, 77, 40),
+          (8, 8, 1024, 77, 80), (8, 8, 256, 77, 160),
           (4, 10, 4096, 4096, 64), (4, 20, 1024, 1024, 64), (4, 20, 1024, 77, 64)]
 
 if __name__ == "__main__":
@@ -24,18 +26,10 @@ if __name__ == "__main__":
         k = torch.randn(B * Nk, H * D, device="cuda").half()
         v = torch.randn(B * Nk, H * D, device="cuda").half()
         out = torch.empty_like(q)
-        fn = lambda: ops.attention(q, k, v, B, H, Nq, Nk, D, D ** -0.5, out=out)
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / a.iters * 1e3
+        probs = torch.empty(B * H, Nq, (Nk + 7) // 8 * 8, device="cuda", dtype=torch.float16) if Nk <= 128 else None
+        fn = lambda: ops.attention(q, k, v, B, H, Nq, Nk, D, D ** -0.5, out=out, probs_out=probs)
+        us = time_us(fn, a.iters)
         fl = 4.0 * B * H * Nq * Nk * D
         tiles = B * H * ((Nq + 127) // 128) * ((Nk + 127) // 128)
-        print(f"[{i}] B={B} H={H} Nq={Nq} Nk={Nk} D={D}: {us:9.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  "
+        print(f"[{i}] B={B} H={H} Nq={Nq} Nk={Nk} D={D}{' +capture' if probs is not None else ''}: {us:9.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  "
               f"{us * 1e-6 * 1.9e9 * 148 / tiles:7.0f} SM-cycles/tile")

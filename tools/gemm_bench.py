@@ -9,6 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from invertible_cd_b200 import ops  # noqa: E402
+from tools._timing import time_us  # noqa: E402
 from invertible_cd_b200.packing import pack_geglu  # noqa: E402
 
 SHAPES = [  # (kind, M, N, K, extras)
@@ -60,16 +61,7 @@ def main():
             out = torch.empty(M, N, device=dev, dtype=torch.float16)
             fn = lambda: ops.conv3x3(x, w, B, HW, HW, bias=bias, out=out, force_bn=args.bn, force_bm=args.bm)
             flops = 2.0 * M * N * K * 9
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / args.iters * 1e3
+        us = time_us(fn, args.iters)
         print(f"[{idx:2d}] {kind:4s} M={M:6d} N={N:5d} K={K * (9 if kind == 'conv' else 1):6d} {extra:9s} "
               f"bn={ops.pick_bn(M, N, 1, 'geglu' in extra, False, 256 if 'geglu' in extra else args.bn):3d} "
               f"{us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s")

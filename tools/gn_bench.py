@@ -7,6 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from invertible_cd_b200 import ops  # noqa: E402
+from tools._timing import time_us  # noqa: E402
 
 if __name__ == "__main__":
     B = 8
@@ -19,16 +20,7 @@ if __name__ == "__main__":
         g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
         out = torch.empty(B * HW, C, device="cuda", dtype=torch.float16)
         fn = lambda: ops.groupnorm(x0, B, HW, g, b, 1e-5, True, ws, x1=x1, out=out)
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / 20 * 1e3
+        us = time_us(fn, 20)
         byt = 2.0 * B * HW * C * 2
         print(f"GN  HW={HW:5d} C={C0}+{C1}: {us:7.1f} us  {byt / us / 1e3:7.1f} GB/s (1R+1W)  {byt / 1e6:6.1f} MB")
     for rows, C in [(32768, 320), (8192, 640), (2048, 1280)]:
@@ -36,15 +28,6 @@ if __name__ == "__main__":
         g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
         out = torch.empty_like(x)
         fn = lambda: ops.layernorm(x, g, b, 1e-5, out=out)
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / 20 * 1e3
+        us = time_us(fn, 20)
         byt = 2.0 * rows * C * 2
         print(f"LN  rows={rows:6d} C={C}: {us:7.1f} us  {byt / us / 1e3:7.1f} GB/s")
