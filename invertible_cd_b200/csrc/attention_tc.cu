@@ -8,16 +8,21 @@
 // written out in the same pass (AttentionStore capture, utils/p2p.py:145-149) instead of being materialised by a
 // separate GEMM + softmax.
 //
-// One CTA = one (batch, head, 128-query tile); K/V stream through a 2-stage TMA ring in 128-key tiles.
+// One CTA = one (batch, head, 128-query tile); K/V stream through a TMA ring in 64-key tiles.
 //   warp 0      TMA producer
-//   warp 1      MMA issuer:  S = Q.K^T  (M128 x N128 x D)  ->  TMEM[0,128)
-//                            O += P.V   (M128 x D x K128)   ->  TMEM[128,128+D)   (V consumed MN-major from smem)
-//   warps 2..5  softmax: one thread per query row; S read from TMEM twice (max pass, exp pass) to keep registers
-//               low enough for 2 CTAs/SM (the second CTA's MMAs fill the tensor pipe while this one does softmax);
-//               P written to 128B-swizzled smem as the A operand of the second MMA; O rescaled in TMEM only when
-//               a row maximum moved.
+//   warp 1      MMA issuer:  S = Q.K^T  (M128 x N64 x D)   ->  TMEM S[j&1]       (A = Q from TENSOR MEMORY)
+//                            O += P.V   (M128 x D x K64)    ->  TMEM O            (A = P from TENSOR MEMORY,
+//                                                                                  V consumed MN-major from smem)
+//                            L += P.1   (M128 x 16 x K64)   ->  TMEM L            (row sums on the tensor core)
+//   warps 2..5  softmax: one thread per query row == one TMEM lane; S read once from TMEM, P = exp2(..) packed to
+//               half2 and written back over the first 32 columns of the S buffer it came from; O rescaled in TMEM
+//               only when a row maximum moved by more than 2^8.
+// Both A operands live in tensor memory: an SS-mode M128 MMA re-reads its 4 KB A slice from shared memory every K16
+// step, i.e. 32 cycles of the 128 B/clk port, so with N <= 64 it is smem-bound (measured, tools/probes/mma_probe.cu:
+// 39/44/48 cycles for N = 16/48/64 where the tensor pipe needs 8/24/32).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/icd_b200.h"
@@ -38,25 +43,49 @@ struct AttnParams {
   long long probs_ld;
 };
 
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial
+// for 2^f (max relative error 7.5e-5, below half an fp16 ulp), exponent added with an integer shift-add.
+// The softmax is MUFU.EX2-bound (16 lanes/clk/SM); computing a fixed fraction of every row's exponentials this way
+// moves work to pipes that are otherwise idle during the exponential phase.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -120.0f);                        // keeps the biased exponent positive; 2^-120 rounds to 0 in fp16
+  const float t = x + 12582912.0f;              // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  const float pl = fmaf(fmaf(fmaf(0.0551716648f, f, 0.2426111251f), f, 0.6932609677f), f, 0.9999280572f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ float exp2_mufu(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+
 template <int D>
 struct AttnCfg {
   static constexpr int DP = (D + 15) / 16 * 16;      // MMA extent along the head dim
   static constexpr int DATOMS = (D + 63) / 64;       // 64-wide (128 B) swizzle atoms along the head dim
   static constexpr int BKV = 64;                     // keys per K/V tile
-  static constexpr int KV_STAGES = DATOMS == 1 ? 4 : (DATOMS == 2 ? 4 : 2);
+  static constexpr int KV_STAGES = DATOMS == 1 ? 4 : (DATOMS == 2 ? 4 : 3);
   static constexpr int Q_BYTES = DATOMS * 16384;     // 128 query rows
   static constexpr int KV_BYTES = DATOMS * 8192;     // 64 key rows
-  static constexpr int P_BYTES = 2 * 16384;          // double-buffered 128 x 64 fp16 probabilities
-  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + P_BYTES + 384;   // + barriers, ones tile
-  static constexpr int TMEM_COLS = (128 + DP + 16) <= 256 ? 256 : 512;   // S0 | S1 | O | 16 row-sum columns
+  static constexpr int KV_RING_BYTES = 2 * KV_STAGES * KV_BYTES;
+  static constexpr int SMEM_BYTES = Q_BYTES + KV_RING_BYTES + 384;   // + barriers, ones tile
+  // TMEM columns: S0/P0 (64) | S1/P1 (64) | O (DP) | L (16) | Q (32 per 64-wide atom of the head dim)
+  static constexpr int TMEM_USED = 128 + DP + 16 + DATOMS * 32;
+  static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
+  static_assert(TMEM_USED <= 512, "TMEM budget");
+  static_assert(KV_STAGES * KV_BYTES >= 2 * 16384, "K ring doubles as the 128 x 128 probability staging buffer");
   static constexpr int MIN_CTAS = (DATOMS == 1) ? 2 : 1;
 };
 
 // Pipeline (one CTA = one (batch, head, 128-query tile); K/V stream in 64-key tiles through a TMA ring):
-//   S (2 TMEM buffers) and P (2 smem buffers) are double-buffered, so the tensor core computes S_{j+1} = Q.K_{j+1}^T
-//   while the softmax warps are still working on tile j, and P_j.V_j runs while they start on tile j+1.
+//   S is double-buffered in TMEM and P_j overwrites the head of S_j, so the tensor core computes
+//   S_{j+1} = Q.K_{j+1}^T while the softmax warps are still working on tile j, and P_j.V_j runs while they start on
+//   tile j+1. tcgen05.mma ops of one thread execute in issue order, which is what makes the aliasing safe:
+//   Q.K_{j+2}^T (overwrites S[j&1] = P_j) is issued after P_j.V_j.
 //   warp 0: TMA producer | warp 1: MMA issuer | warps 2..5: softmax (one thread per query row, S read ONCE from TMEM)
-template <int D>
+// POLY = how many of every 8 exponentials are evaluated by exp2_poly instead of MUFU.EX2
+template <int D, int POLY>
 __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -66,18 +95,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + ST * Cfg::KV_BYTES;
-  uint8_t* sP = sV + ST * Cfg::KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::KV_BYTES);
   uint64_t* q_full = bars;                 // 1
   uint64_t* k_full = bars + 1;             // ST
   uint64_t* v_full = k_full + ST;          // ST
   uint64_t* kv_empty = v_full + ST;        // ST   (P.V of the tile consumed K and V)
   uint64_t* s_full = kv_empty + ST;        // 2    (Q.K^T landed in S[b])
-  uint64_t* p_full = s_full + 2;           // 2    (128 softmax threads wrote P[b]; they are also done reading S[b])
-  uint64_t* pv_done = p_full + 2;          // 2    (P[b].V finished: P[b] reusable, O/L quiescent)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* p_full = s_full + 2;           // 2    (128 softmax threads replaced S[b] by P[b] in TMEM)
+  uint64_t* pv_done = p_full + 2;          // 2    (P[b].V finished: O/L quiescent)
+  uint64_t* q_ready = pv_done + 2;         // 1    (128 softmax threads moved their Q row from smem to TMEM)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_ready + 1);
   uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars) + 256;   // one 8x8 fp16 core matrix of 1.0 (128 B)
-  static_assert((1 + 3 * ST + 6) * 8 + 4 <= 256, "barrier block overflows into the ones tile");
+  static_assert((1 + 3 * ST + 7) * 8 + 4 <= 256, "barrier block overflows into the ones tile");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = (p.Nq + 127) / 128;
@@ -103,6 +132,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
     }
+    mbar_init(q_ready, 128);
     fence_mbar_init();
   } else if (warp == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -117,6 +147,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   pdl_wait();   // prologue above overlaps the previous kernel's tail; Q/K/V are read below
   const uint32_t tmem_O = tmem_base + 128;
   const uint32_t tmem_L = tmem_O + DP;       // row sums: L = P . 1 accumulated by the tensor core
+  const uint32_t tmem_Q = tmem_L + 16;       // Q tile as packed half2: 32 columns per 64-wide head-dim atom
 
   if (warp == 0) {
     if (elect_one()) {
@@ -146,52 +177,69 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ones operand = a single no-swizzle 8x8 core matrix reused for every (row group, k chunk): LBO=SBO=0
       const uint64_t ones_desc =
           (static_cast<uint64_t>((smem_u32(s_ones) >> 4) & 0x3FFF)) | (static_cast<uint64_t>(1) << 46);
-      // smem descriptors are formed by adding constants to precomputed 32-bit low words (building one from an
-      // address costs ~120 cycles of dependent uniform-datapath ops: more than these small MMAs take)
+      // smem descriptors are formed by adding compile-time constants to two precomputed 32-bit low words
       const uint64_t desc_hi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
-      const uint32_t q_lo0 = ((smem_u32(sQ) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t k_lo0 = ((smem_u32(sK) >> 4) & 0x3FFFu) | (1u << 16);
-      const uint32_t p_lo0 = ((smem_u32(sP) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t v_lo0 = ((smem_u32(sV) >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);   // MN-major: LBO = 8 KB
-      auto issue_qk = [&](int jj) {   // S[jj & 1] = Q . K_jj^T
-        const int st = jj % ST;
-        mbar_wait(&k_full[st], (jj / ST) & 1);
-        tc_fence_after();
+      // The issue loop is the serial link between "softmax of tile j done" and "S of tile j+2 ready", so everything
+      // in it is straight-line with compile-time stage / buffer indices (unrolled over U tiles), and the key tile is
+      // always processed with all four K16 steps: keys beyond N_kv have P == 0 and zero-filled V rows.
+      auto issue_qk = [&](int st, int bsel) {   // S[bsel] = Q . K^T for the K tile in ring stage st
         const uint32_t k_lo = k_lo0 + st * (Cfg::KV_BYTES >> 4);
-        const uint32_t d_s = tmem_base + (jj & 1) * BKV;
+        const uint32_t d_s = tmem_base + bsel * BKV;
 #pragma unroll
         for (int a = 0; a < DATOMS; ++a) {
           const int kk_n = (DP - a * 64) >= 64 ? 4 : (DP - a * 64) / 16;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if (kk < kk_n)
-              umma_f16_ss(d_s, desc_hi | (q_lo0 + a * (16384u >> 4) + kk * 2u),
-                          desc_hi | (k_lo + a * (8192u >> 4) + kk * 2u), idesc_s, (a | kk) != 0);
+              umma_f16_ts(d_s, tmem_Q + a * 32 + kk * 8, desc_hi | (k_lo + a * (8192u >> 4) + kk * 2u), idesc_s,
+                          (a | kk) != 0);
           }
         }
-        umma_commit(&s_full[jj & 1]);
+        umma_commit(&s_full[bsel]);
       };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        // S[(j+1)&1] was last read by the softmax of tile j-1, whose p_full we waited for in iteration j-1
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        const int st = j % ST;
-        mbar_wait(&v_full[st], (j / ST) & 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      constexpr int U = (ST % 2 == 0) ? ST : 2 * ST;
+      mbar_wait(q_ready, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      if (n_kv > 1) {
+        mbar_wait(&k_full[1 % ST], (1 / ST) & 1);
         tc_fence_after();
-        const uint32_t p_lo = p_lo0 + (j & 1) * (16384u >> 4), v_lo = v_lo0 + st * (Cfg::KV_BYTES >> 4);
-        const int valid = min(BKV, p.Nk - j * BKV);
-        const int ksteps = (valid + 15) / 16;
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t pdesc = desc_hi | (p_lo + ks * 2u);
-          umma_f16_ss(tmem_O, pdesc, desc_hi | (v_lo + ks * (2048u >> 4)), idesc_o, (j | ks) != 0);
-          // row sums ride on the tensor core: L[128x16] += P[128xK] . ones[Kx16] (every column = sum_k P)
-          umma_f16_ss(tmem_L, pdesc, ones_desc, idesc_l, (j | ks) != 0);
+        issue_qk(1 % ST, 1);
+      }
+      for (int jb = 0; jb < n_kv; jb += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = jb + u;
+          if (j < n_kv) {
+            const int st = u % ST, bsel = u & 1;
+            mbar_wait(&v_full[st], (jb / ST + u / ST) & 1);
+            mbar_wait(&p_full[bsel], ((jb >> 1) + (u >> 1)) & 1);
+            tc_fence_after();
+            // O += P_j . V_j and L += P_j . 1 (A = P from tensor memory: the head of S[bsel])
+            const uint32_t tmem_P = tmem_base + bsel * BKV;
+            const uint32_t v_lo = v_lo0 + st * (Cfg::KV_BYTES >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (ks != 0) ? 1u : static_cast<uint32_t>(j != 0);
+              umma_f16_ts(tmem_O, tmem_P + ks * 8, desc_hi | (v_lo + ks * (2048u >> 4)), idesc_o, acc);
+              // row sums ride on the tensor core: L[128x16] += P[128xK] . ones[Kx16] (every column = sum_k P)
+              umma_f16_ts(tmem_L, tmem_P + ks * 8, ones_desc, idesc_l, acc);
+            }
+            umma_commit(&kv_empty[st]);
+            umma_commit(&pv_done[bsel]);
+            // S[bsel] = Q . K_{j+2}^T, queued right behind P_j . V_j (which reads P_j from the same columns):
+            // tcgen05.mma ops of one thread execute in issue order
+            if (j + 2 < n_kv) {
+              const int st2 = (u + 2) % ST;
+              mbar_wait(&k_full[st2], (jb / ST + (u + 2) / ST) & 1);
+              tc_fence_after();
+              issue_qk(st2, bsel);
+            }
+          }
         }
-        umma_commit(&kv_empty[st]);
-        umma_commit(&pv_done[j & 1]);
       }
     }
   } else {
@@ -202,8 +250,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = q0 + row;
     float m_run = -INFINITY;
     float alpha_after0 = 1.0f;              // rescale applied after tile 0's P was written (probability capture)
-    const uint32_t p_row = smem_u32(sP) + row * 128;
     const int sw = row & 7;
+    // move this thread's Q row from the 128B-swizzled smem tile into tensor memory (A operand of S = Q.K^T);
+    // rows beyond N_q were zero-filled by TMA
+    mbar_wait(q_full, 0);
+#pragma unroll
+    for (int a = 0; a < DATOMS; ++a) {
+      uint32_t qr[32];
+      const uint32_t q_row = smem_u32(sQ) + a * 16384 + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(qr[4 * c]), "=r"(qr[4 * c + 1]), "=r"(qr[4 * c + 2]), "=r"(qr[4 * c + 3])
+                     : "r"(q_row + ((c ^ sw) << 4)));
+      tmem_st16_u32(tmem_Q + lane_off + a * 32, qr);
+      tmem_st16_u32(tmem_Q + lane_off + a * 32 + 16, qr + 16);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(q_ready);
     for (int j = 0; j < n_kv; ++j) {
       const int bsel = j & 1;
       mbar_wait(&s_full[bsel], (j >> 1) & 1);
@@ -218,22 +283,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int i = 0; i < 64; ++i)
           if (i >= valid) s[i] = -INFINITY;
       }
-      float m0 = fmaxf(s[0], s[1]), m1 = fmaxf(s[2], s[3]);
+      float mx[4] = {fmaxf(s[0], s[1]), fmaxf(s[2], s[3]), fmaxf(s[4], s[5]), fmaxf(s[6], s[7])};
 #pragma unroll
-      for (int i = 4; i < 64; i += 4) {
-        m0 = fmaxf(m0, fmaxf(s[i], s[i + 1]));
-        m1 = fmaxf(m1, fmaxf(s[i + 2], s[i + 3]));
+      for (int i = 8; i < 64; i += 8) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx[c] = fmaxf(mx[c], fmaxf(s[i + 2 * c], s[i + 2 * c + 1]));
       }
-      const float m_tile = fmaxf(m0, m1);
+      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       // Lazy rescale: the reference maximum only moves when the tile maximum exceeds it by more than 2^8 (exp2
       // domain); until then P <= 256 (fine in fp16 with fp32 accumulation) and the TMEM round trip is skipped.
-      float alpha = 1.0f;
-      if ((m_tile - m_run) * p.scale_log2e > 8.0f) {
-        alpha = exp2f((m_run - m_tile) * p.scale_log2e);   // 0 on the first tile (m_run = -inf)
-        m_run = m_tile;
-      }
-      const float m_scaled = m_run * p.scale_log2e;
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      // Common case (no row of the warp moves): one subtract, one compare, one vote.
+      const bool moved = (m_tile - m_run) * p.scale_log2e > 8.0f;
+      if (__any_sync(0xffffffffu, moved)) {
+        float alpha = 1.0f;
+        if (moved) {
+          alpha = exp2f((m_run - m_tile) * p.scale_log2e);   // 0 on the first tile (m_run = -inf)
+          m_run = m_tile;
+        }
+        if (j > 0) {
         // O and L must be quiescent: P_{j-1}.V_{j-1} finished (P_j.V_j cannot start before our p_full arrive)
         mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
@@ -254,27 +321,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         tmem_st_wait();
         if (j == 1) alpha_after0 = alpha;
-      }
-      // P[bsel] was last read by P_{j-2}.V_{j-2}
-      if (j >= 2) mbar_wait(&pv_done[bsel], ((j - 2) >> 1) & 1);
-      // p = exp2(s*scale*log2e - m): one FFMA + one MUFU.EX2 per element, packed to fp16 pairs -> swizzled smem
-      const uint32_t pbuf = p_row + bsel * 16384;
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float e0, e1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(s[cc * 8 + 2 * i], p.scale_log2e, -m_scaled)));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s[cc * 8 + 2 * i + 1], p.scale_log2e, -m_scaled)));
-          const __half2 e = __floats2half2_rn(e0, e1);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&e);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pbuf + ((cc ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]),
-                     "r"(pk[2]), "r"(pk[3])
-                     : "memory");
       }
-      fence_proxy_async_smem();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
+      const float m_scaled = m_run * p.scale_log2e;
+      // p = exp2(s*scale*log2e - m): one FFMA + one MUFU.EX2 per element, packed to half2 and written over the
+      // first 32 columns of S[bsel] (this thread's lane only; all 64 scores are already in registers)
+      // which elements of every group of 8 go to the polynomial: spread out so both instruction streams interleave
+      auto use_poly = [](int idx) constexpr {
+        const int r = idx & 7;
+        return (POLY >= 1 && r == 6) || (POLY >= 2 && r == 3) || (POLY >= 3 && r == 1) || (POLY >= 4 && r == 4);
+      };
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x0 = fmaf(s[2 * i], p.scale_log2e, -m_scaled), x1 = fmaf(s[2 * i + 1], p.scale_log2e, -m_scaled);
+        const float e0 = use_poly(2 * i) ? exp2_poly(x0) : exp2_mufu(x0);
+        const float e1 = use_poly(2 * i + 1) ? exp2_poly(x1) : exp2_mufu(x1);
+        const __half2 e = __floats2half2_rn(e0, e1);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&e);
+      }
+      tmem_st16_u32(tmem_base + lane_off + bsel * BKV, pk);
+      tmem_st16_u32(tmem_base + lane_off + bsel * BKV + 16, pk + 16);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[bsel]);
     }
@@ -291,7 +359,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (p.probs != nullptr && n_kv <= 2) {
       // <= 128 keys: both P tiles are still in smem -> emit the normalised probabilities (AttentionStore capture).
       // Each warp owns 32 consecutive rows whose P was written by its own lanes, so a warp-level sync suffices.
+      // The un-normalised P tiles are still in tensor memory (nothing overwrote S0/S1); stage them through the idle
+      // K ring (every MMA has completed) in the swizzled row layout the coalesced write-out below reads.
       const float sc0 = (n_kv == 2) ? inv * alpha_after0 : inv;   // tile 0 was written before the last rescale
+      for (int t = 0; t < n_kv; ++t) {
+        uint32_t pk[32];
+        tmem_ld32(tmem_base + lane_off + t * BKV, reinterpret_cast<float*>(pk));
+        tmem_ld_wait();
+        const uint32_t dst = smem_u32(sK) + row * 128 + t * 16384;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((cc ^ sw) << 4)), "r"(pk[4 * cc]),
+                       "r"(pk[4 * cc + 1]), "r"(pk[4 * cc + 2]), "r"(pk[4 * cc + 3])
+                       : "memory");
+      }
       __syncwarp();
       if ((p.probs_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(p.probs) & 15) == 0) {
         // coalesced: consecutive lanes write consecutive 16-byte chunks; the whole padded row [0, probs_ld) is
@@ -307,7 +388,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint4 val = make_uint4(0, 0, 0, 0);
           if (t < n_kv) {
             const int rr = row0 + r;
-            const uint32_t addr = smem_u32(sP) + rr * 128 + t * 16384 + ((cc ^ (rr & 7)) << 4);
+            const uint32_t addr = smem_u32(sK) + rr * 128 + t * 16384 + ((cc ^ (rr & 7)) << 4);
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                          : "r"(addr));
@@ -326,7 +407,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
         for (int c = 0; c < p.Nk; ++c) {
           const int t = c >> 6, cc = c & 63;
-          const uint32_t addr = p_row + t * 16384 + (((cc >> 3) ^ sw) << 4) + (cc & 7) * 2;
+          const uint32_t addr = smem_u32(sK) + row * 128 + t * 16384 + (((cc >> 3) ^ sw) << 4) + (cc & 7) * 2;
           unsigned short u;
           asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
           pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * (t == 0 ? sc0 : inv));
@@ -365,19 +446,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <int D>
+template <int D, int POLY>
 static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                             cudaStream_t st) {
   using Cfg = AttnCfg<D>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("attention cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
   const int grid = p.B * p.H * ((p.Nq + 127) / 128);
-  launch_k(attention_tc_kernel<D>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, tq, tk, tv, p);
+  launch_k(attention_tc_kernel<D, POLY>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, tq, tk, tv, p);
   return check_launch("attention_tc");
 }
 
@@ -417,11 +498,24 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   p.probs = reinterpret_cast<__half*>(probs_out);
   p.probs_ld = probs_ld;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const int poly = [] {
+    const char* e = getenv("ICD_ATTN_POLY");   // tuning knob (exponentials per 8 on the FMA pipe): 0, 2, 3 or 4
+    return e ? atoi(e) : 3;
+  }();
+#define ICD_ATTN_CASE(DD)                                                          \
+  case DD:                                                                         \
+    switch (poly) {                                                                \
+      case 0: return launch_attention<DD, 0>(tq, tk, tv, p, st);                   \
+      case 2: return launch_attention<DD, 2>(tq, tk, tv, p, st);                   \
+      case 4: return launch_attention<DD, 4>(tq, tk, tv, p, st);                   \
+      default: return launch_attention<DD, 3>(tq, tk, tv, p, st);                  \
+    }
   switch (D) {
-    case 40: return launch_attention<40>(tq, tk, tv, p, st);
-    case 64: return launch_attention<64>(tq, tk, tv, p, st);
-    case 80: return launch_attention<80>(tq, tk, tv, p, st);
-    case 160: return launch_attention<160>(tq, tk, tv, p, st);
+    ICD_ATTN_CASE(40)
+    ICD_ATTN_CASE(64)
+    ICD_ATTN_CASE(80)
+    ICD_ATTN_CASE(160)
     default: return set_error("icd_attention: unsupported head dim (40, 64, 80, 160)");
   }
+#undef ICD_ATTN_CASE
 }
