@@ -60,37 +60,49 @@ __device__ __forceinline__ float exp2_mufu(float x) {
   return e;
 }
 
-template <int D>
+template <int D, int MT_>
 struct AttnCfg {
   static constexpr int DP = (D + 15) / 16 * 16;      // MMA extent along the head dim
   static constexpr int DATOMS = (D + 63) / 64;       // 64-wide (128 B) swizzle atoms along the head dim
   static constexpr int BKV = 64;                     // keys per K/V tile
-  static constexpr int KV_STAGES = DATOMS == 1 ? 4 : (DATOMS == 2 ? 4 : 3);
-  static constexpr int Q_BYTES = DATOMS * 16384;     // 128 query rows
-  static constexpr int KV_BYTES = DATOMS * 8192;     // 64 key rows
+  // TMEM columns per 128-row query tile: S0/P0 (64) | S1/P1 (64) | O (DP) | L (16) | Q (32 per head-dim atom)
+  static constexpr int TMEM_PER_TILE = 128 + DP + 16 + DATOMS * 32;
+  // MT = query tiles per CTA. MT = 2 (needs d <= 64 for the 512 TMEM columns) fetches every K/V tile once per 256
+  // query rows: it pays when the K/V stream is the limiter (d = 40: 80-byte head rows straddle 128-byte lines, the
+  // TMA moves 160 B per row and the kernel sat at ~6.5 TB/s of L2->SM traffic whatever the softmax did). MT = 1
+  // runs two independent CTAs per SM instead, which balances the tail wave better (d = 64).
+  static constexpr int MT = MT_;
+  static_assert(MT == 1 || 2 * TMEM_PER_TILE <= 512, "two query tiles need 2 x TMEM_PER_TILE <= 512 columns");
+  static constexpr int TILE_COLS = 256;              // TMEM column stride between the two query tiles
+  static constexpr int TMEM_COLS = (MT == 2 || TMEM_PER_TILE > 256) ? 512 : 256;
+  static_assert(TMEM_PER_TILE <= (MT == 2 ? 256 : 512), "TMEM budget");
+  static constexpr int KV_STAGES = DATOMS == 1 ? 6 : (DATOMS == 2 ? 4 : 3);
+  static_assert(KV_STAGES >= 3, "Q.K^T runs two tiles ahead of P.V");
+  static constexpr int Q_TILE_BYTES = DATOMS * 16384;   // 128 query rows
+  static constexpr int Q_BYTES = MT * Q_TILE_BYTES;
+  static constexpr int KV_BYTES = DATOMS * 8192;        // 64 key rows
   static constexpr int KV_RING_BYTES = 2 * KV_STAGES * KV_BYTES;
-  static constexpr int SMEM_BYTES = Q_BYTES + KV_RING_BYTES + 384;   // + barriers, ones tile
-  // TMEM columns: S0/P0 (64) | S1/P1 (64) | O (DP) | L (16) | Q (32 per 64-wide atom of the head dim)
-  static constexpr int TMEM_USED = 128 + DP + 16 + DATOMS * 32;
-  static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
-  static_assert(TMEM_USED <= 512, "TMEM budget");
-  static_assert(KV_STAGES * KV_BYTES >= 2 * 16384, "K ring doubles as the 128 x 128 probability staging buffer");
-  static constexpr int MIN_CTAS = (DATOMS == 1) ? 2 : 1;
+  static constexpr int SMEM_BYTES = Q_BYTES + KV_RING_BYTES + 512;   // + barriers, TMEM pointer, ones tile
+  static_assert(KV_RING_BYTES >= MT * 2 * 16384, "K/V ring doubles as the probability staging buffer");
+  static constexpr int THREADS = 32 * (1 + MT + 4 * MT);   // TMA warp; per query tile: 1 MMA warp + 4 softmax warps
+  static constexpr int MIN_CTAS = (2 * SMEM_BYTES + 2048 <= 227 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
 };
 
-// Pipeline (one CTA = one (batch, head, 128-query tile); K/V stream in 64-key tiles through a TMA ring):
-//   S is double-buffered in TMEM and P_j overwrites the head of S_j, so the tensor core computes
+// Pipeline (one CTA = one (batch, head) x MT 128-query tiles; K/V stream in 64-key tiles through a TMA ring):
+//   per query tile, S is double-buffered in TMEM and P_j overwrites the head of S_j, so the tensor core computes
 //   S_{j+1} = Q.K_{j+1}^T while the softmax warps are still working on tile j, and P_j.V_j runs while they start on
 //   tile j+1. tcgen05.mma ops of one thread execute in issue order, which is what makes the aliasing safe:
-//   Q.K_{j+2}^T (overwrites S[j&1] = P_j) is issued after P_j.V_j.
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2..5: softmax (one thread per query row, S read ONCE from TMEM)
+//   Q.K_{j+2}^T (overwrites S[j&1] = P_j) is issued right after P_j.V_j.
+//   warp 0: TMA producer | warp 1+m: MMA issuer of query tile m | warps 1+MT+4m .. 4+MT+4m: softmax of query tile m
+//   (one thread per query row, S read ONCE from TMEM). The query tiles share nothing but the K/V ring: each has its
+//   own issuer so that neither waits behind the other's softmax.
 // POLY = how many of every 8 exponentials are evaluated by exp2_poly instead of MUFU.EX2
-template <int D, int POLY>
-__global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
+template <int D, int MT_, int POLY>
+__global__ void __launch_bounds__(AttnCfg<D, MT_>::THREADS, AttnCfg<D, MT_>::MIN_CTAS)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using Cfg = AttnCfg<D>;
-  constexpr int DP = Cfg::DP, DATOMS = Cfg::DATOMS, ST = Cfg::KV_STAGES, BKV = Cfg::BKV;
+  using Cfg = AttnCfg<D, MT_>;
+  constexpr int DP = Cfg::DP, DATOMS = Cfg::DATOMS, ST = Cfg::KV_STAGES, BKV = Cfg::BKV, MT = Cfg::MT;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
@@ -99,21 +111,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* q_full = bars;                 // 1
   uint64_t* k_full = bars + 1;             // ST
   uint64_t* v_full = k_full + ST;          // ST
-  uint64_t* kv_empty = v_full + ST;        // ST   (P.V of the tile consumed K and V)
-  uint64_t* s_full = kv_empty + ST;        // 2    (Q.K^T landed in S[b])
-  uint64_t* p_full = s_full + 2;           // 2    (128 softmax threads replaced S[b] by P[b] in TMEM)
-  uint64_t* pv_done = p_full + 2;          // 2    (P[b].V finished: O/L quiescent)
-  uint64_t* q_ready = pv_done + 2;         // 1    (128 softmax threads moved their Q row from smem to TMEM)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_ready + 1);
-  uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars) + 256;   // one 8x8 fp16 core matrix of 1.0 (128 B)
-  static_assert((1 + 3 * ST + 7) * 8 + 4 <= 256, "barrier block overflows into the ones tile");
+  uint64_t* kv_empty = v_full + ST;        // ST      (P.V of every query tile consumed K and V: MT arrivals)
+  uint64_t* s_full = kv_empty + ST;        // 2 x MT  (Q.K^T landed in S[m][b])
+  uint64_t* p_full = s_full + 2 * MT;      // 2 x MT  (128 softmax threads replaced S[m][b] by P[m][b] in TMEM)
+  uint64_t* pv_done = p_full + 2 * MT;     // 2 x MT  (P[m][b].V finished: O/L of tile m quiescent)
+  uint64_t* q_ready = pv_done + 2 * MT;    // MT      (softmax threads moved their Q rows from smem to TMEM)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_ready + MT);
+  uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars) + 384;   // one 8x8 fp16 core matrix of 1.0 (128 B)
+  static_assert((1 + 3 * ST + 7 * MT) * 8 + 4 <= 384, "barrier block overflows into the ones tile");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tiles = (p.Nq + 127) / 128;
+  const int q_tiles = (p.Nq + 128 * MT - 1) / (128 * MT);
   const int qt = blockIdx.x % q_tiles;
   const int bh = blockIdx.x / q_tiles;
   const int h = bh % p.H, b = bh / p.H;
-  const int q0 = qt * 128;
+  const int q0 = qt * 128 * MT;
   const int n_kv = (p.Nk + BKV - 1) / BKV;
 
   pdl_launch_dependents();
@@ -125,18 +137,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < ST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], MT);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2 * MT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
     }
-    mbar_init(q_ready, 128);
+    for (int i = 0; i < MT; ++i) mbar_init(&q_ready[i], 128);
     fence_mbar_init();
   } else if (warp == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
-  } else if (warp == 2) {
+  } else if (warp == 1 + MT) {
     reinterpret_cast<uint32_t*>(s_ones)[lane] = 0x3C003C00u;   // 64 halves of 1.0
     fence_proxy_async_smem();
   }
@@ -145,15 +157,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();   // prologue above overlaps the previous kernel's tail; Q/K/V are read below
-  const uint32_t tmem_O = tmem_base + 128;
-  const uint32_t tmem_L = tmem_O + DP;       // row sums: L = P . 1 accumulated by the tensor core
-  const uint32_t tmem_Q = tmem_L + 16;       // Q tile as packed half2: 32 columns per 64-wide head-dim atom
+  // per query tile m (column offset m * TILE_COLS): S0 | S1 | O | L | Q
+  constexpr uint32_t OFF_O = 128, OFF_L = 128 + DP, OFF_Q = 128 + DP + 16;
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
-      for (int a = 0; a < DATOMS; ++a) tma_load_4d(sQ + a * 16384, &tmQ, q_full, a * 64, h, q0, b);
+      for (int m = 0; m < MT; ++m) {
+#pragma unroll
+        for (int a = 0; a < DATOMS; ++a)   // rows beyond N_q (possibly the whole second tile) are zero-filled
+          tma_load_4d(sQ + m * Cfg::Q_TILE_BYTES + a * 16384, &tmQ, q_full, a * 64, h, q0 + m * 128, b);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
@@ -169,7 +184,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (++stage == ST) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= MT) {
+    const int m = warp - 1;                 // query tile of this issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, BKV, false, false);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, DP, false, true);
@@ -182,72 +198,77 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t k_lo0 = ((smem_u32(sK) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t v_lo0 = ((smem_u32(sV) >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);   // MN-major: LBO = 8 KB
       // The issue loop is the serial link between "softmax of tile j done" and "S of tile j+2 ready", so everything
-      // in it is straight-line with compile-time stage / buffer indices (unrolled over U tiles), and the key tile is
-      // always processed with all four K16 steps: keys beyond N_kv have P == 0 and zero-filled V rows.
-      auto issue_qk = [&](int st, int bsel) {   // S[bsel] = Q . K^T for the K tile in ring stage st
+      // in it is straight-line with compile-time stage / buffer indices (unrolled over U key tiles), and a key tile
+      // is always processed with all four K16 steps: keys beyond N_kv have P == 0 and zero-filled V rows.
+      const uint32_t t0 = tmem_base + m * Cfg::TILE_COLS;
+      uint64_t* s_full_m = s_full + 2 * m;
+      uint64_t* p_full_m = p_full + 2 * m;
+      uint64_t* pv_done_m = pv_done + 2 * m;
+      auto issue_qk = [&](int st, int bsel) {   // S[m][bsel] = Q_m . K^T for the K tile in ring stage st
         const uint32_t k_lo = k_lo0 + st * (Cfg::KV_BYTES >> 4);
-        const uint32_t d_s = tmem_base + bsel * BKV;
 #pragma unroll
         for (int a = 0; a < DATOMS; ++a) {
           const int kk_n = (DP - a * 64) >= 64 ? 4 : (DP - a * 64) / 16;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if (kk < kk_n)
-              umma_f16_ts(d_s, tmem_Q + a * 32 + kk * 8, desc_hi | (k_lo + a * (8192u >> 4) + kk * 2u), idesc_s,
-                          (a | kk) != 0);
+              umma_f16_ts(t0 + bsel * BKV, t0 + OFF_Q + a * 32 + kk * 8,
+                          desc_hi | (k_lo + a * (8192u >> 4) + kk * 2u), idesc_s, (a | kk) != 0);
           }
         }
-        umma_commit(&s_full[bsel]);
+        umma_commit(&s_full_m[bsel]);
       };
       constexpr int U = (ST % 2 == 0) ? ST : 2 * ST;
-      mbar_wait(q_ready, 0);
+      mbar_wait(&q_ready[m], 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_qk(0, 0);
       if (n_kv > 1) {
-        mbar_wait(&k_full[1 % ST], (1 / ST) & 1);
+        mbar_wait(&k_full[1], 0);
         tc_fence_after();
-        issue_qk(1 % ST, 1);
+        issue_qk(1, 1);
       }
       for (int jb = 0; jb < n_kv; jb += U) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = jb + u;
           if (j < n_kv) {
-            const int st = u % ST, bsel = u & 1;
+            const int st = u % ST, bsel = u & 1, st2 = (u + 2) % ST;
+            const bool has2 = j + 2 < n_kv;
             mbar_wait(&v_full[st], (jb / ST + u / ST) & 1);
-            mbar_wait(&p_full[bsel], ((jb >> 1) + (u >> 1)) & 1);
-            tc_fence_after();
-            // O += P_j . V_j and L += P_j . 1 (A = P from tensor memory: the head of S[bsel])
-            const uint32_t tmem_P = tmem_base + bsel * BKV;
+            // K_{j+2} sits in a stage that was released by P.V of tile j+2-ST <= j-1 (already issued)
+            if (has2) mbar_wait(&k_full[st2], (jb / ST + (u + 2) / ST) & 1);
             const uint32_t v_lo = v_lo0 + st * (Cfg::KV_BYTES >> 4);
+            mbar_wait(&p_full_m[bsel], ((jb >> 1) + (u >> 1)) & 1);
+            tc_fence_after();
+            // O += P_j . V_j and L += P_j . 1 (A = P from tensor memory: the head of S[m][bsel])
+            const uint32_t tmem_P = t0 + bsel * BKV;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t acc = (ks != 0) ? 1u : static_cast<uint32_t>(j != 0);
-              umma_f16_ts(tmem_O, tmem_P + ks * 8, desc_hi | (v_lo + ks * (2048u >> 4)), idesc_o, acc);
+              umma_f16_ts(t0 + OFF_O, tmem_P + ks * 8, desc_hi | (v_lo + ks * (2048u >> 4)), idesc_o, acc);
               // row sums ride on the tensor core: L[128x16] += P[128xK] . ones[Kx16] (every column = sum_k P)
-              umma_f16_ts(tmem_L, tmem_P + ks * 8, ones_desc, idesc_l, acc);
+              umma_f16_ts(t0 + OFF_L, tmem_P + ks * 8, ones_desc, idesc_l, acc);
             }
             umma_commit(&kv_empty[st]);
-            umma_commit(&pv_done[bsel]);
-            // S[bsel] = Q . K_{j+2}^T, queued right behind P_j . V_j (which reads P_j from the same columns):
-            // tcgen05.mma ops of one thread execute in issue order
-            if (j + 2 < n_kv) {
-              const int st2 = (u + 2) % ST;
-              mbar_wait(&k_full[st2], (jb / ST + (u + 2) / ST) & 1);
-              tc_fence_after();
-              issue_qk(st2, bsel);
-            }
+            umma_commit(&pv_done_m[bsel]);
+            // S[m][bsel] = Q_m . K_{j+2}^T, queued right behind P_j . V_j (which reads P_j from the same columns)
+            if (has2) issue_qk(st2, bsel);
           }
         }
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue
-    const int quad = warp & 3;
+    const int m = (warp - 1 - MT) >> 2;     // query tile of this warp
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;       // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const int q = q0 + row;
+    const uint32_t t0 = tmem_base + m * Cfg::TILE_COLS + lane_off;
+    uint64_t* s_full_m = s_full + 2 * m;
+    uint64_t* p_full_m = p_full + 2 * m;
+    uint64_t* pv_done_m = pv_done + 2 * m;
+    const int q = q0 + m * 128 + row;
     float m_run = -INFINITY;
     float alpha_after0 = 1.0f;              // rescale applied after tile 0's P was written (probability capture)
     const int sw = row & 7;
@@ -257,26 +278,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int a = 0; a < DATOMS; ++a) {
       uint32_t qr[32];
-      const uint32_t q_row = smem_u32(sQ) + a * 16384 + row * 128;
+      const uint32_t q_row = smem_u32(sQ) + m * Cfg::Q_TILE_BYTES + a * 16384 + row * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(qr[4 * c]), "=r"(qr[4 * c + 1]), "=r"(qr[4 * c + 2]), "=r"(qr[4 * c + 3])
                      : "r"(q_row + ((c ^ sw) << 4)));
-      tmem_st16_u32(tmem_Q + lane_off + a * 32, qr);
-      tmem_st16_u32(tmem_Q + lane_off + a * 32 + 16, qr + 16);
+      tmem_st16_u32(t0 + OFF_Q + a * 32, qr);
+      tmem_st16_u32(t0 + OFF_Q + a * 32 + 16, qr + 16);
     }
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(q_ready);
+    mbar_arrive(&q_ready[m]);
     for (int j = 0; j < n_kv; ++j) {
       const int bsel = j & 1;
-      mbar_wait(&s_full[bsel], (j >> 1) & 1);
+      mbar_wait(&s_full_m[bsel], (j >> 1) & 1);
       tc_fence_after();
       const int valid = min(BKV, p.Nk - j * BKV);
       float s[64];
-      tmem_ld32(tmem_base + lane_off + bsel * BKV, s);
-      tmem_ld32(tmem_base + lane_off + bsel * BKV + 32, s + 32);
+      tmem_ld32(t0 + bsel * BKV, s);
+      tmem_ld32(t0 + bsel * BKV + 32, s + 32);
       tmem_ld_wait();
       if (valid < BKV) {                    // warp-uniform: only the last K/V tile can be partial
 #pragma unroll
@@ -301,32 +322,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           m_run = m_tile;
         }
         if (j > 0) {
-        // O and L must be quiescent: P_{j-1}.V_{j-1} finished (P_j.V_j cannot start before our p_full arrive)
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after();
+          // O and L must be quiescent: P_{j-1}.V_{j-1} finished (P_j.V_j cannot start before our p_full arrive)
+          mbar_wait(&pv_done_m[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < DP + 16; c0 += 16) {
-          float o[16];
-          tmem_ld16(tmem_O + lane_off + c0, o);
-          tmem_ld_wait();
+          for (int c0 = 0; c0 < DP + 16; c0 += 16) {
+            float o[16];
+            tmem_ld16(t0 + OFF_O + c0, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] *= alpha;
-          const uint32_t* r = reinterpret_cast<const uint32_t*>(o);
-          asm volatile(
-              "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
-              "%13, %14, %15, %16};" ::"r"(tmem_O + lane_off + c0),
-              "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-              "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-              : "memory");
-        }
-        tmem_st_wait();
-        if (j == 1) alpha_after0 = alpha;
+            for (int i = 0; i < 16; ++i) o[i] *= alpha;
+            tmem_st16_u32(t0 + OFF_O + c0, reinterpret_cast<const uint32_t*>(o));
+          }
+          tmem_st_wait();
+          if (j == 1) alpha_after0 = alpha;
         }
       }
       const float m_scaled = m_run * p.scale_log2e;
-      // p = exp2(s*scale*log2e - m): one FFMA + one MUFU.EX2 per element, packed to half2 and written over the
-      // first 32 columns of S[bsel] (this thread's lane only; all 64 scores are already in registers)
-      // which elements of every group of 8 go to the polynomial: spread out so both instruction streams interleave
+      // p = exp2(s*scale*log2e - m), packed to half2 and written over the first 32 columns of S[bsel] (this thread's
+      // lane only; all 64 scores are already in registers). POLY of every 8 exponentials take the FMA-pipe
+      // polynomial, spread out so that both instruction streams interleave.
       auto use_poly = [](int idx) constexpr {
         const int r = idx & 7;
         return (POLY >= 1 && r == 6) || (POLY >= 2 && r == 3) || (POLY >= 3 && r == 1) || (POLY >= 4 && r == 4);
@@ -340,47 +355,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const __half2 e = __floats2half2_rn(e0, e1);
         pk[i] = *reinterpret_cast<const uint32_t*>(&e);
       }
-      tmem_st16_u32(tmem_base + lane_off + bsel * BKV, pk);
-      tmem_st16_u32(tmem_base + lane_off + bsel * BKV + 16, pk + 16);
+      tmem_st16_u32(t0 + bsel * BKV, pk);
+      tmem_st16_u32(t0 + bsel * BKV + 16, pk + 16);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[bsel]);
+      mbar_arrive(&p_full_m[bsel]);
     }
     // epilogue: O / l -> fp16 -> global   (l = row sum accumulated by the ones-MMA)
-    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
+    mbar_wait(&pv_done_m[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     float inv;
     {
       float l16[16];
-      tmem_ld16(tmem_L + lane_off, l16);
+      tmem_ld16(t0 + OFF_L, l16);
       tmem_ld_wait();
       inv = 1.f / l16[0];
     }
     if (p.probs != nullptr && n_kv <= 2) {
-      // <= 128 keys: both P tiles are still in smem -> emit the normalised probabilities (AttentionStore capture).
-      // Each warp owns 32 consecutive rows whose P was written by its own lanes, so a warp-level sync suffices.
-      // The un-normalised P tiles are still in tensor memory (nothing overwrote S0/S1); stage them through the idle
-      // K ring (every MMA has completed) in the swizzled row layout the coalesced write-out below reads.
+      // <= 128 keys: emit the normalised probabilities (AttentionStore capture). The un-normalised P tiles are still
+      // in tensor memory (nothing overwrote S0/S1). They are staged through the idle K/V ring in a swizzled row
+      // layout (32 KB per query tile) so that the write-out below is coalesced. The ring is idle for THIS query tile
+      // only once every MMA of the CTA has completed, which the last pv_done of the LAST query tile implies.
+      if (MT > 1) {
+        mbar_wait(&pv_done[2 * (MT - 1) + ((n_kv - 1) & 1)], ((n_kv - 1) >> 1) & 1);
+        tc_fence_after();
+      }
       const float sc0 = (n_kv == 2) ? inv * alpha_after0 : inv;   // tile 0 was written before the last rescale
+      const uint32_t stage_base = smem_u32(sK) + m * 32768;
       for (int t = 0; t < n_kv; ++t) {
         uint32_t pk[32];
-        tmem_ld32(tmem_base + lane_off + t * BKV, reinterpret_cast<float*>(pk));
+        tmem_ld32(t0 + t * BKV, reinterpret_cast<float*>(pk));
         tmem_ld_wait();
-        const uint32_t dst = smem_u32(sK) + row * 128 + t * 16384;
+        const uint32_t dst = stage_base + row * 128 + t * 16384;
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((cc ^ sw) << 4)), "r"(pk[4 * cc]),
                        "r"(pk[4 * cc + 1]), "r"(pk[4 * cc + 2]), "r"(pk[4 * cc + 3])
                        : "memory");
       }
+      // Each warp owns 32 consecutive rows whose P was staged by its own lanes, so a warp-level sync suffices.
       __syncwarp();
       if ((p.probs_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(p.probs) & 15) == 0) {
         // coalesced: consecutive lanes write consecutive 16-byte chunks; the whole padded row [0, probs_ld) is
         // written (masked keys have P == 0, chunks beyond the last tile are zero-filled)
         const int nchunk = static_cast<int>(p.probs_ld >> 3);
         const int row0 = quad * 32;
-        uint4* dst = reinterpret_cast<uint4*>(p.probs + (static_cast<long long>(bh) * p.Nq + q0 + row0) * p.probs_ld);
-        const int rows_valid = p.Nq - (q0 + row0);
+        const int qrow0 = q0 + m * 128 + row0;
+        uint4* dst = reinterpret_cast<uint4*>(p.probs + (static_cast<long long>(bh) * p.Nq + qrow0) * p.probs_ld);
+        const int rows_valid = p.Nq - qrow0;
         for (int idx = lane; idx < 32 * nchunk; idx += 32) {
           const int r = idx / nchunk, ch = idx - r * nchunk;
           const float s0 = __shfl_sync(0xffffffffu, sc0, r), s1 = __shfl_sync(0xffffffffu, inv, r);
@@ -388,7 +410,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint4 val = make_uint4(0, 0, 0, 0);
           if (t < n_kv) {
             const int rr = row0 + r;
-            const uint32_t addr = smem_u32(sK) + rr * 128 + t * 16384 + ((cc ^ (rr & 7)) << 4);
+            const uint32_t addr = stage_base + rr * 128 + t * 16384 + ((cc ^ (rr & 7)) << 4);
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                          : "r"(addr));
@@ -407,7 +429,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __half* pr = p.probs + (static_cast<long long>(bh) * p.Nq + q) * p.probs_ld;
         for (int c = 0; c < p.Nk; ++c) {
           const int t = c >> 6, cc = c & 63;
-          const uint32_t addr = smem_u32(sK) + row * 128 + t * 16384 + (((cc >> 3) ^ sw) << 4) + (cc & 7) * 2;
+          const uint32_t addr = stage_base + row * 128 + t * 16384 + (((cc >> 3) ^ sw) << 4) + (cc & 7) * 2;
           unsigned short u;
           asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
           pr[c] = __float2half_rn(__half2float(__ushort_as_half(u)) * (t == 0 ? sc0 : inv));
@@ -418,7 +440,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll 1
     for (int c0 = 0; c0 < DP; c0 += 16) {
       float o[16];
-      tmem_ld16(tmem_O + lane_off + c0, o);
+      tmem_ld16(t0 + OFF_O + c0, o);
       tmem_ld_wait();
       if (q < p.Nq) {
         __half hv[16];
@@ -446,19 +468,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <int D, int POLY>
+template <int D, int MT, int POLY>
 static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                             cudaStream_t st) {
-  using Cfg = AttnCfg<D>;
+  using Cfg = AttnCfg<D, MT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, MT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("attention cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  const int grid = p.B * p.H * ((p.Nq + 127) / 128);
-  launch_k(attention_tc_kernel<D, POLY>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, tq, tk, tv, p);
+  const int grid = p.B * p.H * ((p.Nq + 128 * Cfg::MT - 1) / (128 * Cfg::MT));
+  launch_k(attention_tc_kernel<D, MT, POLY>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tq, tk, tv, p);
   return check_launch("attention_tc");
 }
 
@@ -498,24 +520,27 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   p.probs = reinterpret_cast<__half*>(probs_out);
   p.probs_ld = probs_ld;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static const int poly = [] {
-    const char* e = getenv("ICD_ATTN_POLY");   // tuning knob (exponentials per 8 on the FMA pipe): 0, 2, 3 or 4
-    return e ? atoi(e) : 3;
-  }();
-#define ICD_ATTN_CASE(DD)                                                          \
-  case DD:                                                                         \
-    switch (poly) {                                                                \
-      case 0: return launch_attention<DD, 0>(tq, tk, tv, p, st);                   \
-      case 2: return launch_attention<DD, 2>(tq, tk, tv, p, st);                   \
-      case 4: return launch_attention<DD, 4>(tq, tk, tv, p, st);                   \
-      default: return launch_attention<DD, 3>(tq, tk, tv, p, st);                  \
-    }
+  // Tuning knobs, fixed per head dim from the sweep in profiles/README.md (r1h); the environment overrides are for
+  // re-running that sweep: ICD_ATTN_POLY = exponentials per 8 on the FMA pipe (0, 2, 3), ICD_ATTN_MT = query tiles
+  // per CTA (1, 2; 2 only for d <= 64).
+  static const int poly_env = [] { const char* e = getenv("ICD_ATTN_POLY"); return e ? atoi(e) : -1; }();
+  static const int mt_env = [] { const char* e = getenv("ICD_ATTN_MT"); return e ? atoi(e) : -1; }();
+#define ICD_ATTN_POLY_SWITCH(DD, MM, DEF)                                          \
+  switch (poly_env >= 0 ? poly_env : DEF) {                                        \
+    case 0: return launch_attention<DD, MM, 0>(tq, tk, tv, p, st);                 \
+    case 2: return launch_attention<DD, MM, 2>(tq, tk, tv, p, st);                 \
+    default: return launch_attention<DD, MM, 3>(tq, tk, tv, p, st);                \
+  }
   switch (D) {
-    ICD_ATTN_CASE(40)
-    ICD_ATTN_CASE(64)
-    ICD_ATTN_CASE(80)
-    ICD_ATTN_CASE(160)
+    case 40:   // self-attention (long K/V stream): two query tiles per CTA; cross-attention: more, smaller CTAs
+      if ((mt_env >= 0 ? mt_env : (Nk > 128 ? 2 : 1)) == 2) { ICD_ATTN_POLY_SWITCH(40, 2, 0) }
+      ICD_ATTN_POLY_SWITCH(40, 1, 3)
+    case 64:
+      if ((mt_env >= 0 ? mt_env : 1) == 2) { ICD_ATTN_POLY_SWITCH(64, 2, 3) }
+      ICD_ATTN_POLY_SWITCH(64, 1, 3)
+    case 80: ICD_ATTN_POLY_SWITCH(80, 1, 3)
+    case 160: ICD_ATTN_POLY_SWITCH(160, 1, 3)
     default: return set_error("icd_attention: unsupported head dim (40, 64, 80, 160)");
   }
-#undef ICD_ATTN_CASE
+#undef ICD_ATTN_POLY_SWITCH
 }
