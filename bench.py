@@ -387,9 +387,18 @@ def main():
                              "frac_of_bf16_sustained": work / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
     gw, gms, gn = agg["gemm_tc"]
     peak_tf = peaks["bf16_tflops_sustained"]
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_h_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if args.workload in tj:
+            traffic = tj[args.workload]["gemm_tc_dram_bytes_per_launch"]
+            traffic_src = "profiles/r1_h_traffic.json (ncu dram__bytes_read+write, average over the step's gemm_tc launches)"
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (all convs + linears)",
                 "achieved": gw / (gms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": gw / (gms * 1e-3) / 1e12 / peak_tf, "traffic": None,
+                "frac": gw / (gms * 1e-3) / 1e12 / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch",
+                "traffic_source": traffic_src, "achieved_flop_per_launch": gw / gn,
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": gn, "ms_per_step_in_kernel": gms,
                 "share_of_eager_step": gms / sum(v[1] for v in agg.values()),
@@ -415,4 +424,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()

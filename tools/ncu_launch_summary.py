@@ -8,30 +8,40 @@ from collections import defaultdict
 
 
 def main(csv_path, shapes_path, top=40):
-    rows = []
     with open(csv_path) as f:
         lines = [l for l in f if not l.startswith("==")]
+    per_id = {}
+    order = []
     for r in csv.DictReader(lines):
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+        i = r["ID"]
+        if i not in per_id:
+            per_id[i] = {"name": r["Kernel Name"], "ns": 0.0, "dram": 0.0}
+            order.append(i)
         val = float(r["Metric Value"].replace(",", ""))
-        unit = r.get("Metric Unit", "ns")
-        ns = val * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1)
-        rows.append((r["Kernel Name"], ns))
+        unit = r.get("Metric Unit", "")
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            per_id[i]["ns"] = val * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1)
+        elif r.get("Metric Name") in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            per_id[i]["dram"] += val * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    rows = [(per_id[i]["name"], per_id[i]["ns"]) for i in order]
+    dram = [per_id[i]["dram"] for i in order]
     shapes = json.load(open(shapes_path))
     total = sum(ns for _, ns in rows)
-    fam = defaultdict(lambda: [0, 0.0])
-    for name, ns in rows:
+    fam = defaultdict(lambda: [0, 0.0, 0.0])
+    for (name, ns), db in zip(rows, dram):
         key = name.split("<")[0].split("(")[0]
         key = key.replace("void ", "").replace("icd::", "")
         if "at::native" in name or "at_cuda" in name:
             key = "torch:" + key[:50]
         fam[key][0] += 1
         fam[key][1] += ns
+        fam[key][2] += db
     print(f"launches {len(rows)}  total {total / 1e6:.3f} ms (serialised, cold-cache: compare shares)")
     print("\n-- by kernel family")
-    for k, (n, ns) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
-        print(f"{ns / 1e6:9.3f} ms  {100 * ns / total:5.1f}%  n={n:5d}  {k}")
+    have_dram = sum(dram) > 0
+    for k, (n, ns, db) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+        extra = f"  dram {db / 1e6:9.1f} MB ({db / max(n, 1) / 1e6:7.3f} MB/launch, {db / max(ns, 1):7.1f} GB/s)" if have_dram else ""
+        print(f"{ns / 1e6:9.3f} ms  {100 * ns / total:5.1f}%  n={n:5d}  {k}{extra}")
     # join tensor-core launches with shapes
     it = {"gemm_tc": iter([s for s in shapes if s["kind"] == "gemm_tc"]),
           "attention_tc": iter([s for s in shapes if s["kind"] == "attention_tc"])}
