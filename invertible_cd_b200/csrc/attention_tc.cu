@@ -22,6 +22,7 @@
 // 39/44/48 cycles for N = 16/48/64 where the tensor pipe needs 8/24/32).
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -41,7 +42,20 @@ struct AttnParams {
   long long out_ld;
   __half* probs;      // optional [B*H][Nq][probs_ld]
   long long probs_ld;
+#ifdef ICD_ATTN_PROFILE
+  long long* prof;    // [MT][8] phase cycle counters of one softmax warp per query tile (debug builds only)
+#endif
 };
+
+// Phase timing of one softmax warp (debug builds: make PROF=1): cycles spent per key tile in
+//   0 wait S | 1 tcgen05.ld | 2 max + rescale decision | 3 (unused) | 4 exponentials | 5 tcgen05.st + arrive
+#ifdef ICD_ATTN_PROFILE
+#define ICD_PROF_DECL long long pt_[7] = {0, 0, 0, 0, 0, 0, 0}, pc_ = clock64();
+#define ICD_PROF_MARK(k) { const long long n_ = clock64(); pt_[k] += n_ - pc_; pc_ = n_; }
+#else
+#define ICD_PROF_DECL
+#define ICD_PROF_MARK(k)
+#endif
 
 // 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial
 // for 2^f (max relative error 7.5e-5, below half an fp16 ulp), exponent added with an integer shift-add.
@@ -290,15 +304,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(&q_ready[m]);
+    ICD_PROF_DECL
     for (int j = 0; j < n_kv; ++j) {
       const int bsel = j & 1;
+      ICD_PROF_MARK(6)
       mbar_wait(&s_full_m[bsel], (j >> 1) & 1);
       tc_fence_after();
+      ICD_PROF_MARK(0)
       const int valid = min(BKV, p.Nk - j * BKV);
       float s[64];
       tmem_ld32(t0 + bsel * BKV, s);
       tmem_ld32(t0 + bsel * BKV + 32, s + 32);
       tmem_ld_wait();
+      ICD_PROF_MARK(1)
       if (valid < BKV) {                    // warp-uniform: only the last K/V tile can be partial
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -339,6 +357,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       const float m_scaled = m_run * p.scale_log2e;
+      ICD_PROF_MARK(2)
+      ICD_PROF_MARK(3)
       // p = exp2(s*scale*log2e - m), packed to half2 and written over the first 32 columns of S[bsel] (this thread's
       // lane only; all 64 scores are already in registers). POLY of every 8 exponentials take the FMA-pipe
       // polynomial, spread out so that both instruction streams interleave.
@@ -357,10 +377,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       tmem_st16_u32(t0 + bsel * BKV, pk);
       tmem_st16_u32(t0 + bsel * BKV + 16, pk + 16);
+      ICD_PROF_MARK(4)
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full_m[bsel]);
+      ICD_PROF_MARK(5)
     }
+#ifdef ICD_ATTN_PROFILE
+    if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && quad == 0 && lane == 0)
+      for (int k = 0; k < 7; ++k) p.prof[m * 8 + k] = pt_[k];
+#endif
     // epilogue: O / l -> fp16 -> global   (l = row sum accumulated by the ones-MMA)
     mbar_wait(&pv_done_m[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
@@ -488,6 +514,20 @@ static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const 
 
 using namespace icd;
 
+#ifdef ICD_ATTN_PROFILE
+static long long* g_prof_buf_last = nullptr;
+extern "C" void icd_attention_prof_dump(int n_kv) {
+  cudaDeviceSynchronize();
+  if (g_prof_buf_last == nullptr) return;
+  const char* names[7] = {"wait S", "tcgen05.ld", "max+decide", "-", "exponentials", "st+arrive", "loop"};
+  for (int m = 0; m < 2; ++m) {
+    printf("  tile %d cycles/key-tile:", m);
+    for (int k = 0; k < 7; ++k) printf("  %s %.0f", names[k], double(g_prof_buf_last[m * 8 + k]) / n_kv);
+    printf("\n");
+  }
+}
+#endif
+
 extern "C" int icd_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
                              int D, long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale,
                              void* probs_out, long long probs_ld, void* stream) {
@@ -519,6 +559,13 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   p.out_ld = out_ld;
   p.probs = reinterpret_cast<__half*>(probs_out);
   p.probs_ld = probs_ld;
+#ifdef ICD_ATTN_PROFILE
+  static long long* prof_buf = nullptr;
+  if (prof_buf == nullptr) cudaMallocManaged(&prof_buf, 16 * sizeof(long long));
+  p.prof = prof_buf;
+  g_prof_buf_last = prof_buf;
+  for (int i = 0; i < 16; ++i) prof_buf[i] = 0;
+#endif
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // Tuning knobs, fixed per head dim from the sweep in profiles/README.md (r1h); the environment overrides are for
   // re-running that sweep: ICD_ATTN_POLY = exponentials per 8 on the FMA pipe (0, 2, 3), ICD_ATTN_MT = query tiles
