@@ -102,9 +102,14 @@ int icd_attention(const void* q, const void* k, const void* v, void* out, int B,
  * Memory-bound kernels (HBM roofline): normalisations, activations, layout, embeddings, update.
  * ------------------------------------------------------------------------------------------------ */
 /* GroupNorm(32 groups) [+ SiLU] over NHWC fp16; optional second source concatenated along C.
- * stats_ws: fp32 workspace of 2*B*groups floats (zeroed by the call). Replaces F.group_norm + F.silu. */
+ * stats_ws: fp32 workspace of B*4096 floats (per-chunk partial sums). Replaces F.group_norm + F.silu
+ * (diffusers ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out).
+ * One launch (single pass: the activation chunk of every CTA stays in shared memory between the statistics and the
+ * normalisation) when the whole tensor fits on chip, otherwise two (statistics, apply). */
 int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, void* y, int B, int HW, int groups, float eps,
                   const float* gamma, const float* beta, int apply_silu, float* stats_ws, void* stream);
+/* Number of kernel launches icd_groupnorm will use for this shape (1 = single pass, 2 = statistics + apply). */
+int icd_groupnorm_launches(int B, int HW, int C);
 /* LayerNorm over the last dim of [rows][C] fp16 -> fp16. Replaces F.layer_norm. */
 int icd_layernorm(const void* x, void* y, int rows, int C, float eps, const float* gamma, const float* beta,
                   void* stream);

@@ -3,6 +3,8 @@
 // are combined in fp64) and the reductions are deterministic (no float atomics to global memory).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "../../include/icd_b200.h"
 #include "host_util.h"
 #include "icd_ptx.cuh"
@@ -191,6 +193,173 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass GroupNorm(+SiLU): one read of x, one write of y, one launch.
+// Each CTA keeps its pixel chunk of one image in shared memory between the statistics pass and the normalisation
+// pass; the per-chunk partial sums of an image are combined through global memory by ALL CTAs of that image, which
+// therefore have to be co-resident: the host launches this kernel only when chunks * B <= SMs * (CTAs per SM that
+// the occupancy calculator grants for this much shared memory), otherwise the two-kernel path above runs.
+// Arrival / departure counters live in a zero-initialised device array and are reset by the last departing CTA of
+// an image, so every launch (and every CUDA-graph replay) starts from zero. pdl_wait() precedes every global access,
+// which also serialises consecutive launches on the counters.
+__device__ unsigned int g_gn_counters[2 * 1024];
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, float* ws) {
+  extern __shared__ uint4 s_x[];               // [rows of this chunk][vpr] 16-byte vectors
+  __shared__ float4 s_part[GN_THREADS];
+  __shared__ float s_mean[32], s_rstd[32];
+  const int C = src.C0 + src.C1;
+  const int vpr = C >> 3;
+  const int rows_per_iter = GN_THREADS / vpr;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int v = threadIdx.x % vpr, r = threadIdx.x / vpr;
+  const bool active = r < rows_per_iter;
+  const int c = v * 8;
+  const int g_lo = c / cpg;
+  const int split = (g_lo + 1) * cpg - c;      // elements j < split belong to g_lo, the rest to g_lo + 1
+  const int rows_per_chunk = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * rows_per_chunk;
+  const int p1 = min(HW, p0 + rows_per_chunk);
+  pdl_wait();
+  // ---- pass 1: global -> shared, partial sums (each thread only ever touches its own smem slots)
+  float sl = 0.f, ql = 0.f, sh = 0.f, qh = 0.f;
+  auto accum = [&](const uint4& raw) {
+    const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = __half2float(h[j]);
+      if (j < split) {
+        sl += x;
+        ql += x * x;
+      } else {
+        sh += x;
+        qh += x * x;
+      }
+    }
+  };
+  if (active) {
+    int pix = p0 + r;
+    for (; pix + 3 * rows_per_iter < p1; pix += 4 * rows_per_iter) {   // four independent 16-byte loads in flight
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        raw[u] = *reinterpret_cast<const uint4*>(
+            gn_vec_ptr(src, static_cast<long long>(b) * HW + pix + u * rows_per_iter, c));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s_x[(pix - p0 + u * rows_per_iter) * vpr + v] = raw[u];
+        accum(raw[u]);
+      }
+    }
+    for (; pix < p1; pix += rows_per_iter) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(gn_vec_ptr(src, static_cast<long long>(b) * HW + pix, c));
+      s_x[(pix - p0) * vpr + v] = raw;
+      accum(raw);
+    }
+  }
+  s_part[threadIdx.x] = make_float4(sl, ql, sh, qh);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // same fixed-order gather as gn_stats_kernel (deterministic: no floating-point atomics anywhere)
+    const int g = threadIdx.x;
+    const int v_first = max(0, (g * cpg - 7 + 7) / 8 - 1);
+    const int v_last = min(vpr - 1, ((g + 1) * cpg - 1) / 8);
+    float s = 0.f, q = 0.f;
+    for (int vv = v_first; vv <= v_last; ++vv) {
+      const int glo = (vv * 8) / cpg;
+      const int sp = (glo + 1) * cpg - vv * 8;
+      for (int rr = 0; rr < rows_per_iter; ++rr) {
+        const float4 pt = s_part[rr * vpr + vv];
+        if (glo == g) {
+          s += pt.x;
+          q += pt.y;
+        } else if (glo + 1 == g && sp < 8) {
+          s += pt.z;
+          q += pt.w;
+        }
+      }
+    }
+    float* o = ws + (static_cast<long long>(b) * chunks + chunk) * 64;
+    __stcg(o + g, s);
+    __stcg(o + 32 + g, q);
+    // ---- publish, then wait until every chunk of this image has published (all of them are resident)
+    __threadfence();
+    __syncwarp();
+    if (g == 0) {
+      atomicAdd(&g_gn_counters[2 * b], 1u);
+      volatile unsigned int* arrive = &g_gn_counters[2 * b];
+      unsigned int spins = 0;
+      while (*arrive < static_cast<unsigned int>(chunks)) {
+        __nanosleep(32);
+        if (++spins > (1u << 24)) asm volatile("trap;");   // > 0.5 s: co-residency was violated; fail loudly, do not hang
+      }
+      __threadfence();
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  // ---- finalize the statistics (every CTA of the image does this redundantly: 8 lanes per group, fp64, fixed order)
+  if (threadIdx.x < 256) {
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
+    double s = 0.0, q = 0.0;
+    const float* w = ws + static_cast<long long>(b) * chunks * 64;
+    for (int i = l; i < chunks; i += 8) {
+      s += static_cast<double>(__ldcg(w + i * 64 + g));
+      q += static_cast<double>(__ldcg(w + i * 64 + 32 + g));
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (l == 0) {
+      const double n = static_cast<double>(HW) * cpg;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+  __syncthreads();
+  // the partials of this image may be overwritten (next launch) only after every CTA has read them: the last CTA
+  // to depart resets both counters
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int d = atomicAdd(&g_gn_counters[2 * b + 1], 1u);
+    if (d == static_cast<unsigned int>(chunks) - 1) {
+      g_gn_counters[2 * b + 1] = 0u;
+      __threadfence();
+      g_gn_counters[2 * b] = 0u;
+    }
+  }
+  if (!active) return;
+  // ---- pass 2: shared -> normalise (+SiLU) -> global
+  float a[8], sft[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    a[j] = s_rstd[g] * gamma[c + j];
+    sft[j] = beta[c + j] - s_mean[g] * a[j];
+  }
+  for (int pix = p0 + r; pix < p1; pix += rows_per_iter) {
+    const uint4 raw = s_x[(pix - p0) * vpr + v];
+    const __half* h = reinterpret_cast<const __half*>(&raw);
+    uint4 outv;
+    __half* o = reinterpret_cast<__half*>(&outv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = __half2float(h[j]) * a[j] + sft[j];
+      if (do_silu) x = silu(x);
+      o[j] = __float2half_rn(x);
+    }
+    *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * HW + pix) * C + c) = outv;
+  }
+}
+
 // one warp per row; values stay in registers between the mean and variance passes
 template <int MAXV>  // max 16-byte vectors per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows,
@@ -280,6 +449,48 @@ __global__ void __launch_bounds__(256) softmax_kernel(__half* __restrict__ x, lo
 
 using namespace icd;
 
+// Chunking of the single-pass GroupNorm: the largest chunk count (<= 64 per image) whose CTAs all fit on the device
+// at once with their pixel chunk in shared memory. Returns false when the tensor is too large to stay on chip.
+static bool gn_fused_plan(int B, int HW, int C, int* chunks_out, size_t* smem_out) {
+  static const bool enabled = [] { const char* e = getenv("ICD_GN_FUSED"); return e == nullptr || atoi(e) != 0; }();
+  if (!enabled || B > 1024 || B < 1 || HW < 1) return false;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS);
+  for (int cps = 4; cps >= 1; --cps) {
+    int fc = (sm_count() * cps) / B;
+    if (fc > GN_MAX_CHUNKS) fc = GN_MAX_CHUNKS;
+    if (fc > max_by_rows) fc = max_by_rows;
+    if (fc > HW) fc = HW;
+    if (fc < 1) continue;
+    const int rows = (HW + fc - 1) / fc;
+    const size_t smem = static_cast<size_t>(rows) * C * 2;
+    if (smem > 220 * 1024) continue;
+    int granted = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&granted, gn_fused_kernel, GN_THREADS, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    if (granted < 1 || static_cast<long long>(fc) * B > static_cast<long long>(granted) * sm_count()) continue;
+    *chunks_out = fc;
+    *smem_out = smem;
+    return true;
+  }
+  return false;
+}
+
+extern "C" int icd_groupnorm_launches(int B, int HW, int C) {
+  int fc = 0;
+  size_t smem = 0;
+  return gn_fused_plan(B, HW, C, &fc, &smem) ? 1 : 2;
+}
+
 extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, void* y, int B, int HW, int groups,
                              float eps, const float* gamma, const float* beta, int apply_silu, float* stats_ws,
                              void* stream) {
@@ -292,15 +503,21 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   if (cpg < 8) return set_error("icd_groupnorm: channels per group < 8 unsupported");
   GnSrc src{reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), C0, x1 != nullptr ? C1 : 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS);
+  // ---- single-pass path: every CTA of an image must be resident at once (see gn_fused_kernel)
+  int fc = 0;
+  size_t fsmem = 0;
+  if (gn_fused_plan(B, HW, C, &fc, &fsmem)) {
+    launch_k(gn_fused_kernel, dim3(fc, B), dim3(GN_THREADS), fsmem, st, src, reinterpret_cast<__half*>(y), HW, cpg, fc,
+             eps, gamma, beta, apply_silu, stats_ws);
+    return check_launch("gn_fused");
+  }
   int chunks = (4 * sm_count() + B - 1) / B;
-  { const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS); if (chunks > max_by_rows) chunks = max_by_rows; }
-  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-  if (chunks > HW) chunks = HW;
-  if (chunks < 1) chunks = 1;
+  if (chunks > max_by_rows) chunks = max_by_rows;
   launch_k(gn_stats_kernel, dim3(chunks, B), dim3(GN_THREADS), 0, st, src, HW, cpg, chunks, stats_ws);
   if (check_launch("gn_stats")) return 1;
   int apply_chunks = (4 * sm_count() + B - 1) / B;
-  { const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS); if (apply_chunks > max_by_rows) apply_chunks = max_by_rows; }
+  if (apply_chunks > max_by_rows) apply_chunks = max_by_rows;
   if (apply_chunks > HW) apply_chunks = HW;
   if (apply_chunks < 1) apply_chunks = 1;
   launch_k(gn_apply_kernel, dim3(apply_chunks, B), dim3(GN_THREADS), 0, st, src, reinterpret_cast<__half*>(y), HW, cpg, chunks,

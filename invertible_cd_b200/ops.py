@@ -179,6 +179,16 @@ def attention(q, k, v, B, H, Nq, Nk, D, scale, out=None, probs_out=None):
     return out
 
 
+_gn_plan_cache = {}
+
+
+def _gn_launches(B, HW, Cc):
+    key = (B, HW, Cc)
+    if key not in _gn_plan_cache:
+        _gn_plan_cache[key] = int(_lib.load().icd_groupnorm_launches(B, HW, Cc))
+    return _gn_plan_cache[key]
+
+
 def groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=None, out=None, groups=32):
     _f16(x0, "x0")
     C0 = x0.shape[1]
@@ -190,7 +200,7 @@ def groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=None, out=None, groups=3
     ev = _prof_begin()
     _lib.check(_lib.load().icd_groupnorm(_ptr(x0), C0, _ptr(x1), C1, _ptr(out), B, HW, groups, float(eps),
                                          _ptr(gamma), _ptr(beta), int(silu), _ptr(ws), _stream()), "icd_groupnorm")
-    _count(2)
+    _count(_gn_launches(B, HW, C0 + C1))
     _prof_end(ev, "groupnorm", 2.0 * B * HW * (C0 + C1) * 2)   # algorithmic bytes: read once + write once
     return out
 

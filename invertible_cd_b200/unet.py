@@ -10,7 +10,9 @@ Data layout in HBM
   activations  fp16 channels-last token matrices [rows*H*W, C]  (an NHWC image IS the transformer token matrix,
                so ResNet blocks and transformer blocks hand tensors to each other without a transpose)
   weights      fp16 [N, K] K-contiguous; 3x3 convs [Cout, (ky,kx,cin)]; q|k|v and k|v projections concatenated;
-               GEGLU rows interleaved per 256-wide N tile; all 22/17 time_emb_proj matrices concatenated into one
+               GEGLU rows interleaved per 256-wide N tile; all 22/17 time_emb_proj matrices concatenated into one;
+               the to_k|to_v matrices of EVERY cross-attention layer concatenated into one (the text context is the
+               same for all of them: one GEMM per forward instead of 16 / 70 launch-bound ones)
   latents      fp32 NCHW at the boundary (what the reference's loop carries)
 """
 import math
@@ -82,6 +84,8 @@ class B200UNet:
         self.temb_ch = boc[0] * 4
         temb_w, temb_b = [], []
         self._temb_off = 0
+        kv_w = []
+        self._kv_off = 0
 
         def conv(prefix):
             return SimpleNamespace(w=pack_conv3x3(g(prefix + ".weight")).to(dev), b=_f32(g(prefix + ".bias"), dev))
@@ -111,9 +115,11 @@ class B200UNet:
                 qkv=torch.cat([pack_linear(g(a1 + f".to_{n}.weight")) for n in "qkv"], 0).to(dev),
                 out1=lin(a1 + ".to_out.0"),
                 q2=pack_linear(g(a2 + ".to_q.weight")).to(dev),
-                kv2=torch.cat([pack_linear(g(a2 + f".to_{n}.weight")) for n in "kv"], 0).to(dev),
+                kv_off=self._kv_off,     # column offset of this layer's [K | V] in the all-layers projection
                 out2=lin(a2 + ".to_out.0"),
                 ff1=SimpleNamespace(w=w1, b=b1), ff2=lin(prefix + ".ff.net.2"))
+            kv_w.extend(pack_linear(g(a2 + f".to_{n}.weight")) for n in "kv")
+            self._kv_off += 2 * C
             self.attn_places += [place, place]
             return blk
 
@@ -170,6 +176,8 @@ class B200UNet:
             self.up.append(blk)
         self.norm_out = norm("conv_norm_out")
         self.conv_out = conv("conv_out")
+        # one GEMM for the to_k / to_v projections of every cross-attention layer (attn2, utils/p2p.py:331-333)
+        self.kv_all = torch.cat(kv_w, 0).to(dev)
         # one GEMM for every ResnetBlock2D.time_emb_proj of the network
         self.temb_all = SimpleNamespace(w=torch.cat([pack_linear(w) for w in temb_w], 0).to(dev),
                                         b=torch.cat([_f32(b, dev) for b in temb_b], 0))
@@ -282,7 +290,7 @@ class B200UNet:
             h = ops.linear(a, blk.out1.w, bias=blk.out1.b, residual=h)
             n = ops.layernorm(h, blk.ln2.g, blk.ln2.b)
             q = ops.linear(n, blk.q2)
-            kv = ops.linear(ctx, blk.kv2)
+            kv = self._kv[:, blk.kv_off:blk.kv_off + 2 * C]
             a = self._attention(q, kv[:, :C], kv[:, C:], B, heads, HW, n_ctx, d, True, place)
             h = ops.linear(a, blk.out2.w, bias=blk.out2.b, residual=h)
             n = ops.layernorm(h, blk.ln3.g, blk.ln3.b)
@@ -308,6 +316,7 @@ class B200UNet:
         self._cond_only = cond_only
         self._gn_ws = torch.empty(rows * 4096, device=dev, dtype=torch.float32)
         self._temb = self._time_embed(rows, timestep, timestep_cond, added_cond_kwargs)
+        self._kv = ops.linear(ctx, self.kv_all)     # [rows*77, sum over layers of 2C]: K | V of every attn2
 
         x = ops.conv3x3(ops.latent_to_nhwc(lat, cpad=8), self.conv_in.w, rows, H, W, bias=self.conv_in.b)
         skips = [(x, H, W)]
@@ -344,7 +353,7 @@ class B200UNet:
                         upd_x=x_t, upd_out=nxt, upd_coefs=(a_t, s_t, a_s, s_s))
         else:
             ops.conv3x3(x, self.conv_out.w, rows, H, W, bias=self.conv_out.b, nchw_out=eps)
-        self._temb = None
+        self._temb = self._kv = None
         if not return_dict:
             return (eps,) if nxt is None else (eps, nxt)
         out = UNetOutput(sample=eps)

@@ -221,7 +221,10 @@ def test_upsample2x(ops):
 
 # --------------------------------------------------------------------------- norms / softmax / elementwise
 @pytest.mark.parametrize("B,HW,C0,C1,silu", [(2, 4096, 320, 0, True), (3, 256, 1280, 1280, True),
-                                             (2, 1024, 640, 320, False), (1, 64, 2560, 0, True)])
+                                             (2, 1024, 640, 320, False), (1, 64, 2560, 0, True),
+                                             (8, 1024, 640, 0, True),       # single-pass kernel, 4 CTAs per SM
+                                             (8, 4096, 640, 320, True),     # too large to stay on chip: two kernels
+                                             (5, 200, 320, 0, False)])      # ragged pixel chunks
 def test_groupnorm(ops, B, HW, C0, C1, silu):
     x0 = _rand(B * HW, C0, seed=40) + 0.5
     x1 = _rand(B * HW, C1, scale=2.0, seed=41) if C1 else None
@@ -236,6 +239,27 @@ def test_groupnorm(ops, B, HW, C0, C1, silu):
     if silu:
         ref = F.silu(ref)
     _close(y, ref.permute(0, 2, 1).reshape(B * HW, Cc), what="groupnorm")
+    # the single-pass kernel synchronises the CTAs of an image through counters that the last CTA resets:
+    # back-to-back launches and a CUDA-graph replay must give the same bits
+    y2 = ops.groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=x1)
+    y3 = ops.groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=x1)
+    assert torch.equal(y, y2) and torch.equal(y, y3)
+    out = torch.empty_like(y)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=x1, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=x1, out=out)
+        ops.groupnorm(out, B, HW, gamma, beta, eps, silu, ws, out=torch.empty_like(out)) if C1 == 0 else None
+    for _ in range(3):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, y)
 
 
 @pytest.mark.parametrize("rows,Cc", [(1000, 320), (77, 640), (4096, 1280)])
