@@ -108,6 +108,12 @@ struct TileChoice { int bm, bn, splits; };
 static TileChoice pick_tile(int M, int N, int Z, int num_kb, int geglu, int b_mn_major, int force_bn, int force_bm,
                             int max_splits = 1) {
   const int sms = sm_count();
+  // Measured override (tools/gemm_bench.py #15, #18-#20; profiles/r1i_gemm_qkv_tile_sweep.txt): the Q|K|V projections
+  // (fat N, K = C <= 1280). The model below prefers 256-row tiles for them, but 256x256 and 256x160 tiles fill the
+  // TMEM (single-buffered accumulator), so after every short main loop the epilogue and the burst of output writes
+  // that all CTAs issue together are exposed; 128x256 with double-buffered accumulators is 8-32 % faster.
+  if (force_bn == 0 && force_bm == 0 && !geglu && !b_mn_major && Z == 1 && N >= 1536 && M >= 2048 && num_kb < 48)
+    return TileChoice{128, 256, 1};
   const int bns[4] = {256, 160, 128, 64};
   const int bms[2] = {128, 256};
   TileChoice best{128, 128, 1};

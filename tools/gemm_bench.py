@@ -26,6 +26,15 @@ SHAPES = [  # (kind, M, N, K, extras)
     ("conv", 512, 1280, 1280, "8"),
     ("conv", 512, 1280, 2560, "8"),
     ("lin", 4096, 4096, 4096, ""),
+    # SDXL (B=4, 1024^2): the 32x32 level of the transformer stacks
+    ("lin", 4096, 1280, 1280, "bias+res"),
+    ("lin", 4096, 1280, 5120, "bias+res"),
+    ("lin", 4096, 3840, 1280, ""),
+    ("lin", 4096, 10240, 1280, "geglu"),
+    ("lin", 16384, 640, 640, "bias+res"),
+    ("lin", 16384, 1920, 640, ""),
+    ("lin", 8192, 1920, 640, ""),
+    ("lin", 2048, 3840, 1280, ""),
 ]
 
 
