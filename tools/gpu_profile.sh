@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu launch lists (duration + DRAM bytes per launch) of one eager iCD step, SD1.5 and SDXL, joined with shapes.
 mkdir -p gpurun_out
-M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
+M="${METRICS:-gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum}"
 for W in sd15 sdxl; do
   timeout 900 ncu --nvtx --nvtx-include "icd_step/" --metrics $M --clock-control none --csv \
       --log-file gpurun_out/${TAG}_${W}_launches.csv python bench.py --workload $W --profile-step > gpurun_out/prof_$W.log 2>&1
