@@ -293,7 +293,7 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
       unsigned int spins = 0;
       while (*arrive < static_cast<unsigned int>(chunks)) {
         __nanosleep(32);
-        if (++spins > (1u << 24)) asm volatile("trap;");   // > 0.5 s: co-residency was violated; fail loudly, do not hang
+        if (++spins > (1u << 27)) asm volatile("trap;");   // > 4 s: co-residency was violated; fail loudly, do not hang
       }
       __threadfence();
     }
