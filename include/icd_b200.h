@@ -105,7 +105,10 @@ int icd_attention(const void* q, const void* k, const void* v, void* out, int B,
  * stats_ws: fp32 workspace of B*4096 floats (per-chunk partial sums). Replaces F.group_norm + F.silu
  * (diffusers ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out).
  * One launch (single pass: the activation chunk of every CTA stays in shared memory between the statistics and the
- * normalisation) when the whole tensor fits on chip, otherwise two (statistics, apply). */
+ * normalisation) when the whole tensor fits on chip, otherwise two (statistics, apply).
+ * The single-pass kernel synchronises the CTAs of an image through a per-device counter array: like the reference
+ * (one stream, one in-flight call per pipeline), do not run two icd_groupnorm calls concurrently on different
+ * streams of the same device (set ICD_GN_FUSED=0 to force the two-kernel path if you must). */
 int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, void* y, int B, int HW, int groups, float eps,
                   const float* gamma, const float* beta, int apply_silu, float* stats_ws, void* stream);
 /* Number of kernel launches icd_groupnorm will use for this shape (1 = single pass, 2 = statistics + apply). */
