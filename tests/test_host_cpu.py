@@ -362,3 +362,35 @@ def test_product_does_not_import_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_executor_packs_all_cross_attention_kv_projections_into_one_matrix():
+    """B200UNet._pack concatenates to_k | to_v of every attn2 layer (the text context is shared by all of them) and
+    records each layer's column offset: the slices must be exactly the original weights, in execution order."""
+    from invertible_cd_b200 import arch
+    from invertible_cd_b200.unet import B200UNet
+    cfg = arch.small_sd15_config()
+    sd = arch.synthetic_state_dict(cfg, seed=5)
+    net = B200UNet(cfg, sd, device="cpu")
+    blocks = []
+    for blk in net.down:
+        for t in (blk.attns or []):
+            blocks += [(t.C, b) for b in t.blocks]
+    blocks += [(net.mid.attn.C, b) for b in net.mid.attn.blocks]
+    for blk in net.up:
+        for t in (blk.attns or []):
+            blocks += [(t.C, b) for b in t.blocks]
+    assert len(blocks) == net.num_attention_layers // 2
+    assert net.kv_all.shape == (sum(2 * c for c, _ in blocks), cfg.cross_attention_dim)
+    offs = [b.kv_off for _, b in blocks]
+    assert offs == sorted(offs) and offs[0] == 0
+    keys = [k[:-len(".attn2.to_k.weight")] for k in sd if k.endswith(".attn2.to_k.weight")]
+    seen = 0
+    for prefix in keys:
+        wk, wv = sd[prefix + ".attn2.to_k.weight"].half(), sd[prefix + ".attn2.to_v.weight"].half()
+        C = wk.shape[0]
+        hits = [b for c, b in blocks if c == C and torch.equal(net.kv_all[b.kv_off:b.kv_off + C], wk)
+                and torch.equal(net.kv_all[b.kv_off + C:b.kv_off + 2 * C], wv)]
+        assert len(hits) == 1, prefix
+        seen += 1
+    assert seen == len(blocks)
