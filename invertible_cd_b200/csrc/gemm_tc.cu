@@ -104,6 +104,11 @@ int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], cons
 // Tile-shape heuristic. Every operand byte is fetched from L2 by each CTA that needs it, and a 128x160 tile at
 // full tensor rate would need ~31 TB/s of L2->SM traffic (measured cap ~12 TB/s, profiles/r1_c_*), so the model
 // charges each K block max(MMA time, L2 time) and prefers 256-row tiles (two MMA halves share one B tile).
+// gemm2sm_tc.cu
+bool gemm2sm_wanted(int M, int N, int K, bool geglu);
+int launch_gemm2sm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, int M, int N, int num_kb,
+                   const float* bias, bool geglu, cudaStream_t st);
+
 struct TileChoice { int bm, bn, splits; };
 static TileChoice pick_tile(int M, int N, int Z, int num_kb, int geglu, int b_mn_major, int force_bn, int force_bm,
                             int max_splits = 1) {
@@ -439,6 +444,20 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
       const uint64_t rstr[3] = {(uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2};
       if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, box, 64, 2)) return 1;
     }
+  }
+
+  // Large plain / GEGLU linears: one 256x256 tile per CTA pair (tcgen05.mma.cta_group::2, gemm2sm_tc.cu) where the
+  // measurements say it beats the single-CTA kernel
+  if (p.epi_tma && g->a_mode == GEMM_A_TILED && g->a1 == nullptr && g->Z == 1 && !g->b_mn_major &&
+      g->residual == nullptr && g->rowvec == nullptr && g->alpha == 1.0f && g->force_bm == 0 && g->force_splits == 0 &&
+      (g->force_bn == 0 || g->force_bn == 256) && g->a_z1_stride == 0 && g->a_z2_stride == 0 &&
+      g->b_z1_stride == 0 && g->b_z2_stride == 0 && gemm2sm_wanted(g->M, g->N, g->K0, g->geglu != 0)) {
+    CUtensorMap tmB2;
+    const uint64_t dims[4] = {(uint64_t)g->K0, (uint64_t)g->N, 1, 1};
+    const uint64_t str[3] = {(uint64_t)g->b_ld * 2, (uint64_t)g->b_ld * 2, (uint64_t)g->b_ld * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};   // each CTA of the pair loads half of the 256-row B tile
+    if (make_tmap_4d(&tmB2, g->b, dims, str, box, 128, 2)) return 1;
+    return launch_gemm2sm(tmA0, tmB2, tmOut, g->M, g->N, p.num_kb, g->bias, g->geglu != 0, st);
   }
 
   if (g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR && g->residual == nullptr && g->rowvec == nullptr &&

@@ -57,6 +57,26 @@ def test_linear_256row_tiles(ops, M, K, N, bn):
     _close(out32, a.float() @ w.float().t() + bias, rtol=1e-4, atol=1e-3, what="bm256 fp32")
 
 
+@pytest.mark.parametrize("M,K,N,geglu,bias", [(2048, 1280, 2560, True, True), (4096, 1024, 5120, True, False),
+                                              (4096, 1280, 3840, False, False), (4096, 1024, 4096, False, True),
+                                              (8192, 2048, 3840, False, True)])
+def test_linear_two_sm_tiles(ops, M, K, N, geglu, bias):
+    """Shapes icd_gemm routes to the 2-SM kernel (one 256x256 tile per CTA pair, tcgen05.mma.cta_group::2): GEGLU
+    projections with K >= 1024 and fat-N plain projections. Several tiles per pair, both accumulator buffers."""
+    from invertible_cd_b200.packing import pack_geglu
+    a, w = _rand(M, K, seed=11), _rand(N, K, scale=K ** -0.5, seed=12)
+    b = torch.randn(N, device="cuda") if bias else None
+    y = a.float() @ w.float().t() + (b if bias else 0)
+    if geglu:
+        wp, bp = pack_geglu(w, b if bias else torch.zeros(N, device="cuda"), 256)
+        out = ops.linear(a, wp, bias=bp if bias else None, geglu=True, force_bn=256)
+        ref = y[:, :N // 2] * F.gelu(y[:, N // 2:])
+    else:
+        out = ops.linear(a, w, bias=b)
+        ref = y
+    _close(out, ref, rtol=2e-3, atol=4e-3, what=f"2-SM {M}x{K}x{N} geglu={geglu}")
+
+
 @pytest.mark.parametrize("splits,bm", [(3, 0), (4, 256), (0, 0)])
 def test_split_k(ops, splits, bm):
     """Few-tile, deep-K problems (the 8x8-level convs): K split over CTAs, fp32 partials + fused reduce epilogue."""
