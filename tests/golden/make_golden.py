@@ -118,6 +118,25 @@ def main():
     solver2.latent2image = lambda latents, return_type='np': None
     _, inv = solver2.cons_inversion(lat[:1].clone(), guidance_scale=0.0, w_embed_dim=512, seed=7)
     G["cons_inversion"] = dict(out=inv[0].clone())
+    # ---- (j) teacher DDIM path: prev_step / next_step / guided_step / ddim_loop, classic CFG
+    pipe3 = tiny_pipeline(seed=3)
+    solver3 = rgen.Generator(model=pipe3, n_steps=8, noise_scheduler=DDIMScheduler(), forward_cons_model=pipe3,
+                             reverse_cons_model=pipe3, reverse_timesteps=[259, 519, 779, 999],
+                             forward_timesteps=[19, 259, 519, 779])
+    solver3.context = torch.cat([torch.zeros_like(ctx[:1]), ctx[:1]])
+    gen = torch.Generator().manual_seed(31)
+    e3, x3 = torch.randn(1, 4, 16, 16, generator=gen), torch.randn(1, 4, 16, 16, generator=gen)
+    steps = {tt: (solver3.prev_step(e3, tt, x3).clone(), solver3.next_step(e3, tt, x3).clone()) for tt in (876, 501, 126, 1)}
+    fwd = solver3.ddim_loop(lat[:1].clone(), n_steps=8, is_forward=True, guidance_scale=1.0)
+    rev = solver3.ddim_loop(fwd[-1].clone(), n_steps=8, is_forward=False, guidance_scale=7.5, dynamic_guidance=True,
+                            tau1=0.4, tau2=0.8)
+    rev_static = solver3.ddim_loop(fwd[-1].clone(), n_steps=3, is_forward=False, guidance_scale=3.0)
+    a_, b_ = torch.randn(1, 4, 8, 8, generator=gen), torch.randn(1, 4, 8, 8, generator=gen)
+    G["ddim"] = dict(eps=e3, x=x3, steps=steps, timesteps=pipe3.scheduler.timesteps.clone(),
+                     fwd=[o.clone() for o in fwd], rev=[o.clone() for o in rev], rev_static=[o.clone() for o in rev_static],
+                     guided=dict(text=a_, uncond=b_,
+                                 out={(tt, dyn): rgen.guided_step(a_, b_, tt, 7.5, dyn, 0.4, 0.8).clone()
+                                      for tt in (999, 700, 500, 100) for dyn in (False, True)}))
     # ---- (f) edit controllers on synthetic probabilities, (g) aligner
     tok = ToyTokenizer()
     rp2p.tokenizer, rp2p.device, rp2p.NUM_DDIM_STEPS = tok, "cpu", 4

@@ -189,6 +189,39 @@ def test_cons_inversion_matches_reference_loop(G):
     torch.testing.assert_close(inv[0], G["cons_inversion"]["out"], rtol=1e-5, atol=1e-6)
 
 
+def test_teacher_ddim_path_matches_reference(G):
+    """prev_step / next_step / guided_step / ddim_loop (50-step teacher sampling and DDIM
+    inversion, here with 8 steps) against what the reference's own Generator computes on the same oracle U-Net
+    (utils/generation.py:158-205, 305-343), classic CFG (w_embed_dim = 0) with and without dynamic guidance."""
+    ref = G["ddim"]
+    pipe = tiny_pipe(seed=3)
+    solver = generation.Generator(model=pipe, n_steps=8, noise_scheduler=DDPMScheduler(), forward_cons_model=pipe,
+                                  reverse_cons_model=pipe, reverse_timesteps=[259, 519, 779, 999],
+                                  forward_timesteps=[19, 259, 519, 779])
+    assert torch.equal(torch.as_tensor(pipe.scheduler.timesteps), torch.as_tensor(ref["timesteps"]))
+    for tt, (prev, nxt) in ref["steps"].items():
+        torch.testing.assert_close(solver.prev_step(ref["eps"], tt, ref["x"]), prev, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(solver.next_step(ref["eps"], tt, ref["x"]), nxt, rtol=1e-6, atol=1e-6)
+    gd = ref["guided"]
+    for (tt, dyn), out in gd["out"].items():
+        torch.testing.assert_close(generation.guided_step(gd["text"], gd["uncond"], tt, 7.5, dyn, 0.4, 0.8), out,
+                                   rtol=1e-6, atol=1e-6)
+    ctx = G["cons_generation"]["ctx"][:1]
+    solver.init_prompt(ctx, torch.zeros(1, 77, 96))
+    lat = G["cons_generation"]["lat"][:1]
+    fwd = solver.ddim_loop(lat.clone(), n_steps=8, is_forward=True, guidance_scale=1.0)
+    assert len(fwd) == 9
+    for a, b in zip(fwd, ref["fwd"]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    rev = solver.ddim_loop(ref["fwd"][-1].clone(), n_steps=8, is_forward=False, guidance_scale=7.5,
+                           dynamic_guidance=True, tau1=0.4, tau2=0.8)
+    for a, b in zip(rev, ref["rev"]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=2e-6)
+    rev_s = solver.ddim_loop(ref["fwd"][-1].clone(), n_steps=3, is_forward=False, guidance_scale=3.0)
+    for a, b in zip(rev_s, ref["rev_static"]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=2e-6)
+
+
 def test_runner_overrides_dynamic_guidance_and_shares_noise():
     pipe = tiny_pipe()
     solver = _solver(pipe)
