@@ -181,6 +181,60 @@ def main():
     # ---- (i) SDXL (t, s) pair construction and DDIMSolver endpoints
     solver_xl = rxl.DDIMSolver(acp.numpy(), timesteps=1000, ddim_timesteps=50, num_endpoints=4, num_inverse_endpoints=4)
     G["xl_solver"] = dict(endpoints=solver_xl.endpoints.clone(), inverse=solver_xl.inverse_endpoints.clone())
+    # ---- (k) SDXL loops: the reference's sample_deterministic / inverse_sample_deterministic
+    # on a tiny SDXL-topology oracle U-Net behind a stub pipeline (the VAE / image processor / Img2Img prepare_latents
+    # are stubs: only the loops, the (t, s) pairs, the w-embedding, the dynamic-guidance prompt swap and the update
+    # come from the reference)
+    from types import SimpleNamespace
+    from oracle import unet_oracle as O
+
+    def xl_pipe(seed):
+        torch.manual_seed(seed)
+        unet = O.UNet2DConditionModel(O.tiny_sdxl_config(time_cond_proj_dim=512)).eval()
+        sch = DDIMScheduler()
+
+        def prepare_latents(image, timestep, batch_size, num_images_per_prompt, dtype, device, generator=None):
+            init = image.to(device=device, dtype=dtype)                       # 4-channel inputs are latents already
+            noise = torch.randn(init.shape, generator=generator, dtype=dtype)
+            return sch.add_noise(init, noise, torch.as_tensor(timestep).reshape(1))
+
+        vae = SimpleNamespace(to=lambda *a, **k: None, config=SimpleNamespace(scaling_factor=0.13025),
+                              decode=lambda z, return_dict=False: (z[:, :3],))
+        return SimpleNamespace(unet=unet, scheduler=sch, vae=vae, vae_scale_factor=8,
+                               _execution_device=torch.device("cpu"), prepare_latents=prepare_latents,
+                               image_processor=SimpleNamespace(postprocess=lambda img, **k: None))
+
+    gen = torch.Generator().manual_seed(41)
+    emb = {p_: dict(prompt_embeds=torch.randn(1, 77, 128, generator=gen), text_embeds=torch.randn(1, 64, generator=gen))
+           for p_ in ("src", "edit", "other")}
+
+    def embed_fn(prompts, sizes, crops):
+        return dict(prompt_embeds=torch.cat([emb[p_]["prompt_embeds"] for p_ in prompts]),
+                    text_embeds=torch.cat([emb[p_]["text_embeds"] for p_ in prompts]),
+                    time_ids=torch.tensor([list(sz) + list(c) + [1024, 1024] for sz, c in zip(sizes, crops)],
+                                          dtype=torch.float32))
+
+    xl = {"emb": emb}
+    lat2 = torch.randn(2, 4, 16, 16, generator=gen)
+    pipe_xl = xl_pipe(5)
+    _, out = rxl.sample_deterministic(pipe_xl, ["edit", "other"], latents=lat2.clone(), num_inference_steps=4,
+                                      timesteps=[249, 499, 699, 999], guidance_scale=7.0, compute_embeddings_fn=embed_fn,
+                                      is_sdxl=True, return_latent=True)
+    xl["gen4"] = dict(lat=lat2, out=out.clone())
+    _, out = rxl.sample_deterministic(pipe_xl, ["edit"], latents=lat2[:1].clone(), num_inference_steps=3,
+                                      timesteps=[339, 699, 999], guidance_scale=19.0, compute_embeddings_fn=embed_fn,
+                                      is_sdxl=True, return_latent=True, use_dynamic_guidance=True, tau1=0.8, tau2=0.8,
+                                      amplify_prompt=["src"])
+    xl["edit3_dynamic"] = dict(out=out.clone())
+    _, out = rxl.sample_deterministic(pipe_xl, ["edit"], latents=lat2[:1].clone(), num_inference_steps=4,
+                                      guidance_scale=7.0, compute_embeddings_fn=embed_fn, is_sdxl=True, return_latent=True)
+    xl["gen4_solver_endpoints"] = dict(out=out.clone())
+    inv, start = rxl.inverse_sample_deterministic(pipe_xl, lat2[:1].clone(), ["src"], num_inference_steps=3,
+                                                  timesteps=[19, 339, 699], guidance_scale=0.0,
+                                                  compute_embeddings_fn=embed_fn, is_sdxl=True, seed=9,
+                                                  return_start_latent=True)
+    xl["invert3"] = dict(out=inv.clone(), start=start.clone())
+    G["sdxl_loops"] = xl
     out_path = os.path.join(HERE, "icd_golden.pt")
     torch.save(G, out_path)
     print("wrote", out_path, os.path.getsize(out_path), "bytes")

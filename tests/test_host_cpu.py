@@ -222,6 +222,45 @@ def test_teacher_ddim_path_matches_reference(G):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=2e-6)
 
 
+def test_sdxl_loops_match_reference(G):
+    """sample_deterministic / inverse_sample_deterministic against the reference's own loops
+    (utils/generation_sdxl.py:204-473) on the same tiny SDXL-topology oracle U-Net: explicit and solver-derived
+    (t, s) pairs, w-embedding, dynamic guidance with the source-prompt swap above tau (config 5), forward inversion
+    from noised latents."""
+    ref = G["sdxl_loops"]
+    emb = ref["emb"]
+
+    def embed_fn(prompts, sizes, crops):
+        return dict(prompt_embeds=torch.cat([emb[p]["prompt_embeds"] for p in prompts]),
+                    text_embeds=torch.cat([emb[p]["text_embeds"] for p in prompts]),
+                    time_ids=torch.tensor([list(sz) + list(c) + [1024, 1024] for sz, c in zip(sizes, crops)],
+                                          dtype=torch.float32))
+
+    torch.manual_seed(5)
+    unet = O.UNet2DConditionModel(O.tiny_sdxl_config(time_cond_proj_dim=512)).eval()
+    pipe = ICDPipeline(unet, DDIMScheduler(), device="cpu")
+    lat = ref["gen4"]["lat"]
+    _, out = generation_sdxl.sample_deterministic(pipe, ["edit", "other"], latents=lat.clone(), num_inference_steps=4,
+                                                  timesteps=[249, 499, 699, 999], guidance_scale=7.0,
+                                                  compute_embeddings_fn=embed_fn, is_sdxl=True, return_latent=True)
+    torch.testing.assert_close(out, ref["gen4"]["out"], rtol=1e-5, atol=2e-6)
+    _, out = generation_sdxl.sample_deterministic(pipe, ["edit"], latents=lat[:1].clone(), num_inference_steps=3,
+                                                  timesteps=[339, 699, 999], guidance_scale=19.0,
+                                                  compute_embeddings_fn=embed_fn, is_sdxl=True, return_latent=True,
+                                                  use_dynamic_guidance=True, tau1=0.8, tau2=0.8, amplify_prompt=["src"])
+    torch.testing.assert_close(out, ref["edit3_dynamic"]["out"], rtol=1e-5, atol=2e-6)
+    _, out = generation_sdxl.sample_deterministic(pipe, ["edit"], latents=lat[:1].clone(), num_inference_steps=4,
+                                                  guidance_scale=7.0, compute_embeddings_fn=embed_fn, is_sdxl=True,
+                                                  return_latent=True)
+    torch.testing.assert_close(out, ref["gen4_solver_endpoints"]["out"], rtol=1e-5, atol=2e-6)
+    inv, start = generation_sdxl.inverse_sample_deterministic(pipe, lat[:1].clone(), ["src"], num_inference_steps=3,
+                                                              timesteps=[19, 339, 699], guidance_scale=0.0,
+                                                              compute_embeddings_fn=embed_fn, is_sdxl=True, seed=9,
+                                                              return_start_latent=True)
+    torch.testing.assert_close(start, ref["invert3"]["start"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(inv, ref["invert3"]["out"], rtol=1e-5, atol=2e-6)
+
+
 def test_runner_overrides_dynamic_guidance_and_shares_noise():
     pipe = tiny_pipe()
     solver = _solver(pipe)
