@@ -261,6 +261,30 @@ def test_sdxl_loops_match_reference(G):
     torch.testing.assert_close(inv, ref["invert3"]["out"], rtol=1e-5, atol=2e-6)
 
 
+def test_invert_dispatch(G):
+    """utils/inversion.py::invert (SURVEY 8a row 11): consistency vs DDIM branch, NPI list, NTI refusal, and the
+    DummyController registration on the teacher (controller=None)."""
+    from invertible_cd_b200 import inversion
+    pipe = tiny_pipe()
+    pipe.unet.num_attention_layers = 32     # duck-type the executor surface p2p.register_attention_control needs
+    pipe.unet.controller = "stale"
+    solver = _solver(pipe)
+    ctx = G["cons_generation"]["ctx"][:1]
+    lat = G["cons_generation"]["lat"][:1]
+    solver.init_prompt(ctx, torch.zeros(1, 77, 96))
+    (gt, rec), inv, uncond = inversion.invert(solver, stop_step=50, is_cons_inversion=True, inv_guidance_scale=0.0,
+                                              w_embed_dim=512, image_path=lat.clone(), prompt=ctx, seed=7)
+    torch.testing.assert_close(inv, G["cons_inversion"]["out"], rtol=1e-5, atol=1e-6)
+    assert uncond is None and torch.equal(gt, lat)
+    assert pipe.unet.controller is None     # invert detaches any controller from the teacher (DummyController)
+    (_, _), inv2, uncond2 = inversion.invert(solver, stop_step=3, is_cons_inversion=False, inv_guidance_scale=1.0,
+                                             image_path=lat.clone(), prompt=ctx, do_npi=True)
+    assert inv2.shape == lat.shape and len(uncond2) == solver.n_steps
+    assert all(torch.equal(u, solver.context.chunk(2)[1]) for u in uncond2)
+    with pytest.raises(NotImplementedError, match="null-text"):
+        inversion.invert(solver, stop_step=3, image_path=lat.clone(), prompt=ctx, do_nti=True)
+
+
 def test_runner_overrides_dynamic_guidance_and_shares_noise():
     pipe = tiny_pipe()
     solver = _solver(pipe)
