@@ -235,6 +235,15 @@ def main():
                                                   return_start_latent=True)
     xl["invert3"] = dict(out=inv.clone(), start=start.clone())
     G["sdxl_loops"] = xl
+    # ---- (l) SDXL prompt encoding (row 21) with toy tokenizers / encoders: hidden_states[-2] of both encoders
+    # concatenated, pooled output of the last one, time_ids layout
+    from toy_tokenizer import ToyCallableTokenizer, ToyTextEncoder
+    toks = [ToyCallableTokenizer(), ToyCallableTokenizer()]
+    encs = [ToyTextEncoder(24, 1), ToyTextEncoder(40, 2, pooled_dim=16)]
+    prompts_xl = ["a photo of a squirrel eating a burger", ["a house on a mountain", "unused alternative"]]
+    ce = rxl.compute_embeddings(prompts_xl, [(1024, 1024), (768, 512)], [(0, 0), (8, 16)], 0.0, encs, toks,
+                                is_train=False, device="cpu")
+    G["xl_embed"] = {k: v.clone() for k, v in ce.items()}
     out_path = os.path.join(HERE, "icd_golden.pt")
     torch.save(G, out_path)
     print("wrote", out_path, os.path.getsize(out_path), "bytes")

@@ -285,6 +285,23 @@ def test_invert_dispatch(G):
         inversion.invert(solver, stop_step=3, image_path=lat.clone(), prompt=ctx, do_nti=True)
 
 
+def test_sdxl_prompt_embeddings_match_reference(G):
+    """utils/generation_sdxl.py:9-76 (row 21) with toy tokenizers / text encoders: hidden_states[-2] of both encoders
+    concatenated, pooled output of the last encoder, time_ids = [orig_h, orig_w, crop_t, crop_l, 1024, 1024]."""
+    from toy_tokenizer import ToyCallableTokenizer, ToyTextEncoder
+    toks = [ToyCallableTokenizer(), ToyCallableTokenizer()]
+    encs = [ToyTextEncoder(24, 1), ToyTextEncoder(40, 2, pooled_dim=16)]
+    prompts = ["a photo of a squirrel eating a burger", ["a house on a mountain", "unused alternative"]]
+    got = generation_sdxl.compute_embeddings(prompts, [(1024, 1024), (768, 512)], [(0, 0), (8, 16)], 0.0, encs, toks,
+                                             is_train=False, device="cpu")
+    ref = G["xl_embed"]
+    assert set(got) == set(ref) == {"prompt_embeds", "text_embeds", "time_ids"}
+    for k in ref:
+        assert got[k].dtype == ref[k].dtype and got[k].shape == ref[k].shape, k
+        torch.testing.assert_close(got[k], ref[k], rtol=0, atol=0)
+    assert got["prompt_embeds"].shape == (2, 77, 64) and got["time_ids"][1].tolist() == [768, 512, 8, 16, 1024, 1024]
+
+
 def test_runner_overrides_dynamic_guidance_and_shares_noise():
     pipe = tiny_pipe()
     solver = _solver(pipe)
