@@ -498,12 +498,12 @@ template <int D, int MT, int POLY>
 static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                             cudaStream_t st) {
   using Cfg = AttnCfg<D, MT>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.cur()) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, MT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("attention cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    configured = true;
+    configured.cur() = true;
   }
   const int grid = p.B * p.H * ((p.Nq + 128 * Cfg::MT - 1) / (128 * Cfg::MT));
   launch_k(attention_tc_kernel<D, MT, POLY>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tq, tk, tv, p);

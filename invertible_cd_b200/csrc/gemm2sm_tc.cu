@@ -277,11 +277,11 @@ gemm2sm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <bool GEGLU>
 int launch_2sm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const Gemm2smParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.cur()) {
     cudaError_t e = cudaFuncSetAttribute(gemm2sm_tc_kernel<GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e != cudaSuccess) return set_error(std::string("gemm2sm cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    configured = true;
+    configured.cur() = true;
   }
   const int tiles = (p.M / 256) * (p.N / 256);
   const int pairs = sm_count() / 2;

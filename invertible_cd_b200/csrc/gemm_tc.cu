@@ -167,12 +167,12 @@ template <int BM, int BN, int EPI>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                   const CUtensorMap& r, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BM, BN, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.cur()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BM, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    configured = true;
+    configured.cur() = true;
   }
   const long long tiles = static_cast<long long>((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.Z * p.splits;
   int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());

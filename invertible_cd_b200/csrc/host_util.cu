@@ -10,19 +10,27 @@ int set_error(const std::string& msg) {
   g_err = msg;
   return 1;
 }
+int device_ordinal() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return dev;
+}
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
-      n = prop.multiProcessorCount;
+  static int n[kMaxDevices] = {};
+  const int dev = device_ordinal() & (kMaxDevices - 1);
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n[dev] = v;
     else {
       cudaGetLastError();
       return 148;
     }
   }
-  return n;
+  return n[dev];
 }
 static int g_pdl = -1;
 bool pdl_enabled() {

@@ -6,7 +6,15 @@
 
 namespace icd {
 int set_error(const std::string& msg);  // records the message, returns 1
-int sm_count();                          // SMs of the current device (148 on B200); 148 if no device is visible
+int sm_count();                          // SMs of the CURRENT device (148 on B200); 148 if no device is visible
+int device_ordinal();                    // cudaGetDevice (0 if no device is visible)
+constexpr int kMaxDevices = 64;
+// One-time-per-DEVICE flag (cudaFuncSetAttribute and friends are per device, not per process): a library loaded
+// once may serve several GPUs of one process (load_models(model_id, 'cuda:1', ...)).
+struct PerDeviceFlag {
+  bool v[kMaxDevices] = {};
+  bool& cur() { return v[device_ordinal() & (kMaxDevices - 1)]; }
+};
 int check_launch(const char* what);      // cudaGetLastError -> set_error
 bool pdl_enabled();                      // programmatic dependent launch (ICD_PDL=0 or icd_set_pdl(0) disables)
 

@@ -454,13 +454,13 @@ using namespace icd;
 static bool gn_fused_plan(int B, int HW, int C, int* chunks_out, size_t* smem_out) {
   static const bool enabled = [] { const char* e = getenv("ICD_GN_FUSED"); return e == nullptr || atoi(e) != 0; }();
   if (!enabled || B > 1024 || B < 1 || HW < 1) return false;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.cur()) {
     if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    configured = true;
+    configured.cur() = true;
   }
   const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS);
   for (int cps = 4; cps >= 1; --cps) {
@@ -499,8 +499,8 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   if (C % 32 != 0 || C0 % 8 != 0 || (x1 != nullptr && C1 % 8 != 0)) return set_error("icd_groupnorm: bad channels");
   if (C / 8 > GN_THREADS) return set_error("icd_groupnorm: C > 2560 unsupported");
   const int cpg = C / 32;
-  if (cpg < 8 && cpg != 0 && (8 % cpg) != 0) return set_error("icd_groupnorm: channels per group < 8 unsupported");
-  if (cpg < 8) return set_error("icd_groupnorm: channels per group < 8 unsupported");
+  // a 16-byte vector (8 channels) may straddle at most two groups: cpg >= 8, or cpg == 4 (VAE: 128 channels)
+  if (cpg < 8 && cpg != 4) return set_error("icd_groupnorm: channels per group must be 4 or >= 8");
   GnSrc src{reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), C0, x1 != nullptr ? C1 : 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS);
@@ -512,8 +512,12 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
              eps, gamma, beta, apply_silu, stats_ws);
     return check_launch("gn_fused");
   }
+  // stats chunks index the caller's workspace ([B][chunks][2][32] floats, contract: B * 4096 floats): never more
+  // than GN_MAX_CHUNKS per image
   int chunks = (4 * sm_count() + B - 1) / B;
   if (chunks > max_by_rows) chunks = max_by_rows;
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+  if (chunks < 1) chunks = 1;
   launch_k(gn_stats_kernel, dim3(chunks, B), dim3(GN_THREADS), 0, st, src, HW, cpg, chunks, stats_ws);
   if (check_launch("gn_stats")) return 1;
   int apply_chunks = (4 * sm_count() + B - 1) / B;

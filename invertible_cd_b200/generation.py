@@ -19,7 +19,7 @@ from typing import Union
 import numpy as np
 import torch
 
-from . import p2p
+from . import graphs, p2p
 
 
 # ---------------------------------------------------------------------------------------------- entry point
@@ -348,32 +348,70 @@ class Generator:
         return predicted_origin(noise_pred, torch.tensor([t] * n, device=dev), torch.tensor([s] * n, device=dev),
                                 latent, self.model.scheduler.config.prediction_type, alpha_schedule, sigma_schedule)
 
+    def _cons_loop(self, model, latent, timesteps, boundaries, controller, kw):
+        """K consistency steps (t -> s) with `model`; returns the K latents (:388-410 / :430-449)."""
+        alpha_schedule, sigma_schedule = self._schedules()
+        outs = []
+        for t, s in zip(timesteps, boundaries):
+            latent = self._consistency_step(model, latent, t, s, alpha_schedule, sigma_schedule, **kw)
+            if controller is not None:
+                latent = controller.step_callback(latent)
+            outs.append(latent)
+        return outs
+
+    def _cons_loop_maybe_graphed(self, model, latent, timesteps, boundaries, controller, kw):
+        """Replays the whole K-step loop from a cached CUDA graph when its Python side is fully determined by the
+        arguments (graphs.py); otherwise runs it eagerly. Same results either way (deterministic kernels)."""
+        unet = model.unet
+        attn_ctrl = getattr(unet, "controller", None)
+        sig = graphs.controller_signature(attn_ctrl)
+        ok = (graphs.enabled() and getattr(unet, "supports_cond_only", False) and kw.get("w_embed_dim", 0) > 0
+              and sig is not None and (controller is None or controller is attn_ctrl)
+              and latent.is_cuda and self.context is not None and self.context.is_cuda
+              and self.model.scheduler.config.prediction_type == "epsilon"
+              and not torch.cuda.is_current_stream_capturing())
+        if not ok:
+            graphs.stats["eager"] += 1
+            return self._cons_loop(model, latent, timesteps, boundaries, controller, kw)
+        ts, bs = tuple(int(t) for t in timesteps), tuple(int(b) for b in boundaries)
+        key = ("sd15", tuple(latent.shape), latent.dtype, tuple(self.context.shape), self.context.dtype,
+               ts, bs, sig, tuple(sorted((k, float(v) if isinstance(v, (int, float)) else v) for k, v in kw.items())))
+        solver = self
+
+        def body(lat, ctx):
+            proto = graphs.proto_controller(attn_ctrl)
+            saved_ctrl, saved_ctx = unet.controller, solver.context
+            unet.controller, solver.context = proto, ctx
+            try:
+                outs = solver._cons_loop(model, lat, ts, bs, proto if controller is not None else None, kw)
+            finally:
+                unet.controller, solver.context = saved_ctrl, saved_ctx
+            return outs, proto
+
+        with torch.cuda.device(latent.device):
+            outs, proto = graphs.run(unet, key, [latent, self.context], body)
+            graphs.finish_controller(attn_ctrl, proto, len(ts))
+            return [o.clone() for o in outs]
+
     @torch.no_grad()
     def cons_generation(self, latent, guidance_scale=1, dynamic_guidance=False, tau1=0.4, tau2=0.6, w_embed_dim=0,
                         controller=None):
         all_latent = [latent]
         latent = latent.clone().detach()
-        alpha_schedule, sigma_schedule = self._schedules()
-        for t, s in zip(self.reverse_timesteps, self.reverse_boundary_timesteps):
-            latent = self._consistency_step(self.reverse_cons_model, latent, t, s, alpha_schedule, sigma_schedule,
-                                            tau1=tau1, tau2=tau2, w_embed_dim=w_embed_dim,
-                                            guidance_scale=guidance_scale, dynamic_guidance=dynamic_guidance)
-            if controller is not None:
-                latent = controller.step_callback(latent)
-            all_latent.append(latent)
-        return all_latent
+        kw = dict(tau1=tau1, tau2=tau2, w_embed_dim=w_embed_dim, guidance_scale=guidance_scale,
+                  dynamic_guidance=dynamic_guidance)
+        return all_latent + self._cons_loop_maybe_graphed(self.reverse_cons_model, latent, self.reverse_timesteps,
+                                                          self.reverse_boundary_timesteps, controller, kw)
 
     @torch.no_grad()
     def cons_inversion(self, image, guidance_scale=0.0, w_embed_dim=0, seed=0):
-        alpha_schedule, sigma_schedule = self._schedules()
         latent = self.image2latent(image)
         noise = torch.randn(latent.shape, generator=torch.Generator().manual_seed(seed)).to(latent.device)
         latent = self.noise_scheduler.add_noise(latent, noise, torch.tensor([self.start_timestep]))
         image_rec = self.latent2image(latent)
-        for t, s in zip(self.forward_timesteps, self.forward_boundary_timesteps):
-            latent = self._consistency_step(self.forward_cons_model, latent, t, s, alpha_schedule, sigma_schedule,
-                                            guidance_scale=guidance_scale, w_embed_dim=w_embed_dim,
-                                            dynamic_guidance=False)
+        kw = dict(guidance_scale=guidance_scale, w_embed_dim=w_embed_dim, dynamic_guidance=False)
+        latent = self._cons_loop_maybe_graphed(self.forward_cons_model, latent, self.forward_timesteps,
+                                               self.forward_boundary_timesteps, None, kw)[-1]
         return image_rec, [latent]
 
 

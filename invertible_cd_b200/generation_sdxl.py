@@ -136,8 +136,9 @@ def _pairs_from_solver(pipe, num_scales, num_inference_steps, max_inverse_timest
                         ddim_timesteps=num_scales, num_endpoints=num_inference_steps,
                         num_inverse_endpoints=num_inference_steps,
                         max_inverse_timestep_index=max_inverse_timestep_index, endpoints=endpoints,
-                        inverse_endpoints=inverse_endpoints).to(device)
-    return solver.inverse_endpoints.flip(0), solver.endpoints.flip(0)
+                        inverse_endpoints=inverse_endpoints)
+    # the endpoint tables stay on the host: `int(t)` / `t.item()` in the loop must not force a D2H sync per step
+    return solver.inverse_endpoints.cpu().flip(0), solver.endpoints.cpu().flip(0)
 
 
 def _step(pipe, latents, t, s, prompt_embeds, w_embedding, added, alpha_schedule, sigma_schedule):
@@ -179,6 +180,56 @@ def _w_embedding(pipe, w_rows, device, dtype):
     return guidance_scale_embedding(w_rows, embedding_dim=512).to(device=device, dtype=dtype)
 
 
+def _loop_eager(pipe, latents, ts, bs, prompt_embeds, amplify_embeds, added, w_rows, dynamic, tau1, tau2, out_dtype,
+                alpha_schedule, sigma_schedule):
+    """The K (t -> s) steps of both samplers (:286-297 / :431-463): per-step prompt swap + guidance re-embedding
+    under dynamic guidance (source prompt and w -> 0 while t > tau1 * 1000), cast back to `out_dtype` each step."""
+    device = latents.device
+    w_embedding = None if w_rows is None else _w_embedding(pipe, w_rows, device, latents.dtype)
+    embeds = prompt_embeds
+    for t, s in zip(ts, bs):
+        if dynamic:
+            t_item = int(t)
+            embeds = amplify_embeds if (t_item > tau1 * 1000 and amplify_embeds is not None) else prompt_embeds
+            w_embedding = _w_embedding(pipe, [linear_schedule_old(t_item, wi, tau1=tau1, tau2=tau2) for wi in w_rows],
+                                       device, latents.dtype)
+        latents = _step(pipe, latents.to(out_dtype), t, s, embeds, w_embedding, added, alpha_schedule,
+                        sigma_schedule).to(out_dtype)
+    return latents
+
+
+def _loop(pipe, latents, timesteps, boundary, prompt_embeds, amplify_embeds, added, w_rows, dynamic, tau1, tau2,
+          out_dtype, alpha_schedule, sigma_schedule):
+    """Runs `_loop_eager`, replayed from a cached CUDA graph when the U-Net is a B200UNet (graphs.py)."""
+    from . import graphs
+    unet = pipe.unet
+    ts, bs = [int(t) for t in timesteps], [int(b) for b in boundary]
+    tensors = [latents, prompt_embeds] + ([amplify_embeds] if amplify_embeds is not None else [])
+    names = sorted(added) if added else []
+    tensors += [added[k] for k in names]
+    ok = (graphs.enabled() and getattr(unet, "supports_cond_only", False) and getattr(unet, "controller", None) is None
+          and pipe.scheduler.config.prediction_type == "epsilon" and all(torch.is_tensor(x) and x.is_cuda for x in tensors)
+          and not torch.cuda.is_current_stream_capturing())
+    if not ok:
+        graphs.stats["eager"] += 1
+        return _loop_eager(pipe, latents, ts, bs, prompt_embeds, amplify_embeds, added, w_rows, dynamic, tau1, tau2,
+                           out_dtype, alpha_schedule, sigma_schedule)
+    key = ("sdxl", tuple((tuple(x.shape), x.dtype) for x in tensors), tuple(names), amplify_embeds is not None,
+           tuple(ts), tuple(bs), None if w_rows is None else tuple(float(w) for w in w_rows), bool(dynamic),
+           float(tau1), float(tau2), out_dtype)
+    n_fixed = 3 if amplify_embeds is not None else 2
+
+    def body(lat, emb, *rest):
+        amp = rest[0] if amplify_embeds is not None else None
+        add = dict(zip(names, rest[n_fixed - 2:])) if names else added
+        return [_loop_eager(pipe, lat, ts, bs, emb, amp, add, w_rows, dynamic, tau1, tau2, out_dtype, alpha_schedule,
+                            sigma_schedule)], None
+
+    with torch.cuda.device(latents.device):
+        outs, _ = graphs.run(unet, key, tensors, body)
+        return outs[0].clone()
+
+
 # ---------------------------------------------------------------------------------------------- public API
 @torch.no_grad()
 def inverse_sample_deterministic(pipe, images, prompt, generator=None, num_scales=50, num_inference_steps=1,
@@ -202,12 +253,9 @@ def inverse_sample_deterministic(pipe, images, prompt, generator=None, num_scale
     start_latents = _prepare_image_latents(pipe, images, timesteps[0], batch_size, prompt_embeds.dtype, device,
                                            torch.Generator().manual_seed(seed))
     latents = start_latents.clone()
-    w_embedding = None
-    if guidance_scale is not None:
-        w_embedding = _w_embedding(pipe, torch.ones(batch_size) * guidance_scale, device, latents.dtype)
-    for t, s in zip(timesteps, boundary):
-        latents = _step(pipe, latents.to(prompt_embeds.dtype), t, s, prompt_embeds, w_embedding, added,
-                        alpha_schedule, sigma_schedule).to(prompt_embeds.dtype)
+    w_rows = None if guidance_scale is None else [float(guidance_scale)] * batch_size
+    latents = _loop(pipe, latents, timesteps, boundary, prompt_embeds, None, added, w_rows, False, 0.0, 0.0,
+                    prompt_embeds.dtype, alpha_schedule, sigma_schedule)
     return (latents, start_latents) if return_start_latent else latents
 
 
@@ -244,21 +292,11 @@ def sample_deterministic(pipe, prompt, latents=None, generator=None, num_scales=
     else:
         latents = latents.to(device, dtype=prompt_embeds.dtype)
 
-    w_embedding = None
-    w = guidance_scale
+    w_rows = None
     if guidance_scale is not None:
-        w_embedding = _w_embedding(pipe, torch.ones(batch_size) * torch.as_tensor(guidance_scale, dtype=torch.float32),
-                                   device, latents.dtype)
-    for t, s in zip(timesteps, boundary):
-        if use_dynamic_guidance:
-            t_item = t if isinstance(t, int) else t.item()
-            use_src = t_item > tau1 * 1000 and amplify_embeds is not None
-            prompt_embeds = amplify_embeds if use_src else prompt_embeds_init
-            w_vec = torch.ones(batch_size) * torch.as_tensor(w, dtype=torch.float32)
-            w_vec = torch.tensor([linear_schedule_old(t_item, wi.item(), tau1=tau1, tau2=tau2) for wi in w_vec])
-            w_embedding = _w_embedding(pipe, w_vec, device, latents.dtype)
-        latents = _step(pipe, latents, t, s, prompt_embeds, w_embedding, added, alpha_schedule,
-                        sigma_schedule).to(pipe.unet.dtype)
+        w_rows = (torch.ones(batch_size) * torch.as_tensor(guidance_scale, dtype=torch.float32)).tolist()
+    latents = _loop(pipe, latents, timesteps, boundary, prompt_embeds_init, amplify_embeds, added, w_rows,
+                    use_dynamic_guidance, tau1, tau2, pipe.unet.dtype, alpha_schedule, sigma_schedule)
 
     image = None
     if getattr(pipe, "vae", None) is not None:
@@ -280,5 +318,7 @@ def _prepare_image_latents(pipe, images, timestep, batch_size, dtype, device, ge
         init = pipe.vae.encode(images).latent_dist.sample(generator) * pipe.vae.config.scaling_factor
     if init.shape[0] != batch_size:
         init = init.repeat(batch_size // init.shape[0], 1, 1, 1)
-    noise = torch.randn(init.shape, generator=generator).to(device=device, dtype=dtype)
+    # diffusers' randn_tensor draws directly in `dtype` on the generator's (CPU) device: the fp16 normal_ path gives
+    # different values from fp32-then-cast, so the start latent for a given seed only reproduces this way
+    noise = torch.randn(init.shape, generator=generator, dtype=dtype).to(device=device)
     return pipe.scheduler.add_noise(init, noise, torch.as_tensor(timestep).reshape(1))

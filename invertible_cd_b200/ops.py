@@ -32,6 +32,8 @@ def _prof_end(ev, kind, work):
 
 
 def _stream():
+    """torch's current stream of the CURRENT device; the callers (B200UNet.forward, graphs.run) make the tensors'
+    device current first, and `_f16` rejects tensors that live elsewhere."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -47,6 +49,9 @@ def _count(n=1):
 def _f16(t, name):
     if t.dtype != torch.float16 or not t.is_cuda:
         raise ValueError(f"{name}: expected a CUDA fp16 tensor, got {t.dtype} on {t.device}")
+    if t.device.index != torch.cuda.current_device():
+        raise ValueError(f"{name}: tensor lives on {t.device} but the current device is cuda:"
+                         f"{torch.cuda.current_device()} (wrap the call in torch.cuda.device(t.device))")
 
 
 _splitk_ws = {}

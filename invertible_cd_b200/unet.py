@@ -47,6 +47,8 @@ class B200UNet:
     def __init__(self, config, state_dict, device="cuda"):
         self.config = config if not isinstance(config, dict) else SimpleNamespace(**config)
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.controller = None          # set by p2p.register_attention_control
         self.attn_places = []           # execution-ordered ('down'|'mid'|'up') per Attention module
         self._pack(state_dict)
@@ -204,7 +206,8 @@ class B200UNet:
 
     def guidance_embedding(self, w, dim=512):
         """w: fp32 [rows] device tensor -> fp16 [rows, dim] (utils/generation.py:96-122)."""
-        return ops.guidance_embedding(w, self._freqs("w", dim), dim)
+        with torch.cuda.device(self.device):
+            return ops.guidance_embedding(w, self._freqs("w", dim), dim)
 
     def _time_embed(self, rows, timestep, timestep_cond, added):
         dev = self.device
@@ -300,8 +303,14 @@ class B200UNet:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, sample, timestep, encoder_hidden_states=None, timestep_cond=None, added_cond_kwargs=None,
-                cross_attention_kwargs=None, return_dict=True, cond_only=False, update=None):
+    def forward(self, *args, **kwargs):
+        """See `_forward`. Runs with this U-Net's device current: every launch goes to torch's current stream OF
+        THAT DEVICE (`load_models(model_id, 'cuda:1', ...)` works without a prior torch.cuda.set_device)."""
+        with torch.cuda.device(self.device):
+            return self._forward(*args, **kwargs)
+
+    def _forward(self, sample, timestep, encoder_hidden_states=None, timestep_cond=None, added_cond_kwargs=None,
+                 cross_attention_kwargs=None, return_dict=True, cond_only=False, update=None):
         """sample: [rows, 4, H, W] (any float dtype; computed in fp16) -> eps fp32 [rows, 4, H, W].
         `cond_only`: the rows are the conditional half only (controller sees them all).
         `update`: optional (x_t fp32 NCHW, alpha_t, sigma_t, alpha_s, sigma_s): fuse predicted_origin into the
