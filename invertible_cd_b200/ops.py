@@ -13,6 +13,12 @@ from . import _lib
 launch_count = 0  # number of kernel launches issued through this module (bench.py reports it)
 profile = None    # when a list: every tensor-core launch appends (kind, flops, start_event, end_event)
 shape_log = None  # when a list: every gemm / attention launch appends a dict describing its problem
+work = None       # when a dict: algorithmic work per kernel family ("gemm"/"attention": FLOP; "groupnorm"/"layernorm": bytes)
+
+
+def _work(kind, amount):
+    if work is not None:
+        work[kind] = work.get(kind, 0.0) + amount
 
 
 def _prof_begin():
@@ -86,6 +92,7 @@ def gemm_raw(**kw):
     ev = _prof_begin()
     _lib.check(_lib.load().icd_gemm(C.byref(g), _stream()), "icd_gemm")
     _count()
+    _work("gemm", 2.0 * g.M * g.N * g.K * (9 if g.a_mode == 1 else 1) * g.Z)
     if ev is not None:
         k_total = g.K * (9 if g.a_mode == 1 else 1)
         _prof_end(ev, "gemm_tc", 2.0 * g.M * g.N * k_total * g.Z)
@@ -180,6 +187,7 @@ def attention(q, k, v, B, H, Nq, Nk, D, scale, out=None, probs_out=None):
                                          probs_out.stride(1) if probs_out is not None else 0, _stream()),
                "icd_attention")
     _count()
+    _work("attention", 4.0 * B * H * Nq * Nk * D)
     _prof_end(ev, "attention_tc", 4.0 * B * H * Nq * Nk * D)
     return out
 
@@ -206,6 +214,7 @@ def groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=None, out=None, groups=3
     _lib.check(_lib.load().icd_groupnorm(_ptr(x0), C0, _ptr(x1), C1, _ptr(out), B, HW, groups, float(eps),
                                          _ptr(gamma), _ptr(beta), int(silu), _ptr(ws), _stream()), "icd_groupnorm")
     _count(_gn_launches(B, HW, C0 + C1))
+    _work("groupnorm", 2.0 * B * HW * (C0 + C1) * 2)
     _prof_end(ev, "groupnorm", 2.0 * B * HW * (C0 + C1) * 2)   # algorithmic bytes: read once + write once
     return out
 
@@ -218,6 +227,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     _lib.check(_lib.load().icd_layernorm(_ptr(x), _ptr(out), rows, Cc, float(eps), _ptr(gamma), _ptr(beta),
                                          _stream()), "icd_layernorm")
     _count()
+    _work("layernorm", 4.0 * rows * Cc)
     return out
 
 

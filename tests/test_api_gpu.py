@@ -188,3 +188,57 @@ def test_sdxl_sample_and_inverse(sd15_models):
     erri = _rel(goti, refi)
     print("sdxl forward 3-step rel-L2:", erri)
     assert erri <= 2e-2
+
+
+def test_library_graph_cache_equals_eager(sd15_models):
+    """The product path replays the K-step loop from the library's own CUDA-graph cache (graphs.py): results, the
+    AttentionStore state and the step counters must equal the eager run bit for bit, on the capturing call and on
+    later replays with different inputs; edit controllers keep running eagerly."""
+    from invertible_cd_b200 import generation, graphs, inversion, p2p
+    cfg, ldm, rev, fwd, _, _ = sd15_models
+    solver = _solver(ldm, rev, fwd)
+    g = torch.Generator().manual_seed(21)
+
+    def run(seed, use_graphs, self_maps):
+        prev = graphs.set_enabled(use_graphs)
+        try:
+            gg = torch.Generator().manual_seed(seed)
+            ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=gg).half().float()
+            x_T = torch.randn(1, 4, 64, 64, generator=gg)
+            store = p2p.AttentionStore()
+            store.capture_self = self_maps
+            lat, _ = generation.runner(model=rev, prompt=ctx, controller=store, solver=solver, is_cons_forward=True,
+                                       guidance_scale=19.0, latent=x_T, return_type="latent", tau1=0.8, tau2=0.8,
+                                       w_embed_dim=512)
+            torch.cuda.synchronize()
+            return lat, store
+        finally:
+            graphs.set_enabled(prev)
+
+    graphs.clear(rev.unet)
+    before = dict(graphs.stats)
+    for self_maps in (False, True):
+        for seed in (1, 2, 3):                     # seed 1 captures, 2 and 3 replay with new inputs
+            lat_g, st_g = run(seed, True, self_maps)
+            lat_e, st_e = run(seed, False, self_maps)
+            assert torch.equal(lat_g, lat_e)
+            assert st_g.cur_step == st_e.cur_step == 4 and st_g.cur_att_layer == st_e.cur_att_layer == 0
+            assert set(st_g.attention_store) == set(st_e.attention_store)
+            for k in st_e.attention_store:
+                assert len(st_g.attention_store[k]) == len(st_e.attention_store[k]), k
+                for a, b in zip(st_g.attention_store[k], st_e.attention_store[k]):
+                    assert torch.equal(a, b), k
+    assert graphs.stats["captures"] - before["captures"] == 2          # one graph per controller kind
+    assert graphs.stats["replays"] - before["replays"] == 6
+    # forward-consistency inversion (no controller on the forward model) goes through the cache as well
+    img = torch.randn(1, 4, 64, 64, generator=g) * 0.5
+    ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).half().float()
+    outs = []
+    for use in (True, True, False):
+        prev = graphs.set_enabled(use)
+        (_, _), x_inv, _ = inversion.invert(solver, stop_step=50, is_cons_inversion=True, inv_guidance_scale=0.0,
+                                            w_embed_dim=512, image_path=img.cuda(), prompt=ctx, seed=3)
+        graphs.set_enabled(prev)
+        outs.append(x_inv.clone())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[2])
+    p2p.register_attention_control(rev, None)

@@ -282,6 +282,25 @@ def test_groupnorm(ops, B, HW, C0, C1, silu):
         assert torch.equal(out, y)
 
 
+@pytest.mark.parametrize("B,HW,C0,C1", [(8, 4096, 640, 320), (4, 16384, 320, 0), (2, 16384, 128, 0)])
+def test_groupnorm_workspace_contract_two_kernel_path(ops, B, HW, C0, C1):
+    """The two-kernel fallback (tensors too large for the single-pass kernel, or ICD_GN_FUSED=0) must stay inside the
+    documented workspace of B * 4096 floats: canary words right behind it survive (round-1 ADVICE: the statistics
+    kernel used up to 148 chunks per image against a 64-chunk workspace). (2, 16384, 128): 4 channels per group, the
+    VAE's 128-channel level."""
+    x0 = _rand(B * HW, C0, seed=50) + 0.25
+    x1 = _rand(B * HW, C1, seed=51) if C1 else None
+    Cc = C0 + C1
+    gamma, beta = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    buf = torch.full((B * 4096 + 65536,), 12345.0, device="cuda")
+    y = ops.groupnorm(x0, B, HW, gamma, beta, 1e-5, True, buf[:B * 4096], x1=x1)
+    torch.cuda.synchronize()
+    assert bool((buf[B * 4096:] == 12345.0).all()), "GroupNorm wrote past its B*4096-float workspace"
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    ref = F.silu(F.group_norm(x.float().reshape(B, HW, Cc).permute(0, 2, 1), 32, gamma, beta, 1e-5))
+    _close(y, ref.permute(0, 2, 1).reshape(B * HW, Cc), what="groupnorm-2k")
+
+
 @pytest.mark.parametrize("rows,Cc", [(1000, 320), (77, 640), (4096, 1280)])
 def test_layernorm(ops, rows, Cc):
     x = _rand(rows, Cc, seed=42) * 3 + 1

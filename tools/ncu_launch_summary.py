@@ -47,7 +47,8 @@ def main(csv_path, shapes_path, top=40):
           "attention_tc": iter([s for s in shapes if s["kind"] == "attention_tc"])}
     agg = defaultdict(lambda: [0, 0.0, 0.0])
     for name, ns in rows:
-        kind = "gemm_tc" if "gemm_tc_kernel" in name else "attention_tc" if "attention_tc_kernel" in name else None
+        kind = ("gemm_tc" if ("gemm_tc_kernel" in name or "gemm2sm_tc_kernel" in name)
+                else "attention_tc" if "attention_tc_kernel" in name else None)
         if kind is None:
             continue
         try:
@@ -66,5 +67,31 @@ def main(csv_path, shapes_path, top=40):
         print(f"{ns / 1e6:9.3f} ms  {100 * ns / total:5.1f}%  n={n:4d}  {fl / ns / 1e3:8.1f} TFLOP/s  {k}")
 
 
+    return fam
+
+
+FAMILIES = {"gemm": ("gemm_tc_kernel", "gemm2sm_tc_kernel", "splitk_reduce_kernel"), "attention": ("attention_tc_kernel",),
+            "groupnorm": ("gn_fused_kernel", "gn_stats_kernel", "gn_apply_kernel"), "layernorm": ("layernorm_kernel",)}
+
+
 if __name__ == "__main__":
-    main(*sys.argv[1:3])
+    fam = main(*sys.argv[1:3])
+    if len(sys.argv) > 4:
+        # ncu_launch_summary.py launches.csv shapes.json <workload> <traffic.json>: per-family DRAM bytes per launch
+        wl, out = sys.argv[3], sys.argv[4]
+        try:
+            data = json.load(open(out))
+        except Exception:
+            data = {}
+        rec = {"source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the launches of "
+                         f"one eager step ({sys.argv[1].split('/')[-1]})"}
+        for name, pats in FAMILIES.items():
+            n = sum(v[0] for k, v in fam.items() if any(p in k for p in pats))
+            db = sum(v[2] for k, v in fam.items() if any(p in k for p in pats))
+            ns = sum(v[1] for k, v in fam.items() if any(p in k for p in pats))
+            if n:
+                rec[f"{name}_dram_bytes_per_launch"] = db / n
+                rec[f"{name}_launches"] = n
+                rec[f"{name}_ms_serialised"] = ns / 1e6
+        data[wl] = rec
+        json.dump(data, open(out, "w"), indent=1)
