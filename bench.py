@@ -271,6 +271,7 @@ def _build_ours(wl, device):
     if wl["xl"]:
         stable, rev, fwd = loading.load_models_xl(wl["model"], "synthetic:1", "synthetic:2", None, device=device)
         del stable, fwd
+        rev.vae = None        # the metric is latents/s (VAE excluded): sample_deterministic must not decode
         return None, rev, None
     ldm, rev, fwd = loading.load_models(wl["model"], device, "synthetic:1", None, r=64, w_embed_dim=512,
                                         dtype="fp16")
@@ -456,9 +457,19 @@ def measure(wl_key, B, args, rank, world, local_rank, device, full, capture_self
     work = ops.work
     ops.work = None
     peaks, peak_src = _peaks()
-    fam_time, fam_n, total_us, time_src = {}, {}, 0.0, "CUPTI kernel durations of one CUDA-graph replay of the step"
+    fam_time, fam_n, total_us = {}, {}, 0.0
+    time_src = ("CUPTI kernel durations of one CUDA-graph replay of the step captured with programmatic dependent launch "
+                "OFF (with PDL a kernel becomes resident early and its CUPTI duration then includes the wait for its "
+                "predecessor, which double-counts)")
     try:
-        kt = kernel_times_of(graph.replay)
+        from invertible_cd_b200 import _lib
+        prev_pdl = _lib.load().icd_set_pdl(0)
+        try:
+            graph_nopdl, _, _ = capture(capture_self)
+        finally:
+            _lib.load().icd_set_pdl(prev_pdl)
+        kt = kernel_times_of(graph_nopdl.replay)
+        del graph_nopdl
         for name, (n, us) in kt.items():
             total_us += us
             for fam, pats in FAMILIES:

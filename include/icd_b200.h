@@ -122,6 +122,9 @@ int icd_softmax(void* x, long long rows, int cols, long long ld, void* stream);
 int icd_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* gather for the stride-2 3x3 Downsample2D conv: y[B*Ho*Wo][9*C] from NHWC x (pad 1). */
 int icd_im2col_s2(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* same with the low-side padding explicit: pad = 1 is icd_im2col_s2; pad = 0 is the VAE encoder's Downsample2D
+ * (diffusers pads (0,1,0,1) and convolves unpadded: zeros on the bottom / right edge only). */
+int icd_im2col_s2_pad(const void* x, void* y, int B, int H, int W, int C, int pad, void* stream);
 /* NCHW fp32 latent -> NHWC fp16 with channels zero-padded to Cpad (conv_in operand). */
 int icd_latent_to_nhwc(const float* x, void* y, int B, int C, int HW, int Cpad, void* stream);
 /* sinusoidal embeddings: diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) -> [n][dim] fp16 = [cos | sin].

@@ -31,9 +31,11 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
   }
 }
 
-// y[(b,ho,wo)][tap][c] = x[b][2ho+ky-1][2wo+kx-1][c] (zero outside): operand of the stride-2 Downsample2D conv
+// y[(b,ho,wo)][tap][c] = x[b][2ho+ky-pad][2wo+kx-pad][c] (zero outside): operand of the stride-2 Downsample2D conv.
+// pad = 1: the U-Net's Downsample2D (conv padding 1); pad = 0: the VAE encoder's (F.pad(x, (0,1,0,1)) then an
+// unpadded conv, i.e. zeros only on the bottom / right edge).
 __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H,
-                                                        int W, int vpc) {
+                                                        int W, int vpc, int pad) {
   pdl_launch_dependents();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4* __restrict_
     r /= Wo;
     const int ho = static_cast<int>(r % Ho);
     const int b = static_cast<int>(r / Ho);
-    const int hy = 2 * ho + tap / 3 - 1, wx = 2 * wo + tap % 3 - 1;
+    const int hy = 2 * ho + tap / 3 - pad, wx = 2 * wo + tap % 3 - pad;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (hy >= 0 && hy < H && wx >= 0 && wx < W) val = x[((static_cast<long long>(b) * H + hy) * W + wx) * vpc + v];
     y[i] = val;
@@ -156,12 +158,18 @@ extern "C" int icd_upsample2x(const void* x, void* y, int B, int H, int W, int C
   return check_launch("upsample2x");
 }
 
-extern "C" int icd_im2col_s2(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+extern "C" int icd_im2col_s2_pad(const void* x, void* y, int B, int H, int W, int C, int pad, void* stream) {
   if (C % 8 != 0 || (H & 1) || (W & 1)) return set_error("icd_im2col_s2: C % 8 != 0 or odd H/W");
+  if (pad != 0 && pad != 1) return set_error("icd_im2col_s2: pad must be 0 or 1");
   const int vpc = C / 8;
-  launch_k(im2col_s2_kernel, dim3(grid_for(static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * vpc)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint4*>(x),
-                                                               reinterpret_cast<uint4*>(y), B, H, W, vpc);
+  launch_k(im2col_s2_kernel, dim3(grid_for(static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * vpc)), dim3(256), 0,
+           reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), B, H, W,
+           vpc, pad);
   return check_launch("im2col_s2");
+}
+
+extern "C" int icd_im2col_s2(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  return icd_im2col_s2_pad(x, y, B, H, W, C, 1, stream);
 }
 
 extern "C" int icd_latent_to_nhwc(const float* x, void* y, int B, int C, int HW, int Cpad, void* stream) {

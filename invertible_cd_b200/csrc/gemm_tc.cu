@@ -289,10 +289,15 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   CUtensorMap tmA0, tmA1, tmB;
   if (g->a_mode == GEMM_A_CONV3X3) {
     const int H = g->H, W = g->W, B = g->B;
-    if (W > 128 || (128 % W) != 0) return set_error("icd_gemm(conv): W must divide 128");
+    if (W > 128 ? (W % 128) != 0 : (128 % W) != 0)
+      return set_error("icd_gemm(conv): W must divide 128 or be a multiple of it");
     const int hw = H * W;
     int tile_w = W, tile_h, tile_b;
-    if (hw >= 128) {
+    if (W > 128) {   // VAE resolutions (256 .. 1024 wide): one 128-row M tile = 128 consecutive pixels of one image row
+      tile_w = 128;
+      tile_h = 1;
+      tile_b = 1;
+    } else if (hw >= 128) {
       if ((hw % 128) != 0) return set_error("icd_gemm(conv): H*W must be a multiple of 128 (or divide it)");
       tile_h = 128 / W;
       tile_b = 1;

@@ -36,4 +36,26 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// Cooperative launch (+ the same programmatic-stream-serialization attribute): the driver guarantees that every CTA
+// of the grid is resident at once (or refuses the launch), which grid-wide barriers inside the kernel rely on.
+// Measured on B200 (tools/probes/coop_probe.cu, profiles/r2_coop_probe.txt): accepted together with the PDL attribute,
+// eagerly and under stream capture, at no extra cost per launch in a graph.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace icd

@@ -1,6 +1,7 @@
 // HBM-bound normalisation kernels: GroupNorm(+SiLU) over channels-last activations, LayerNorm, row softmax.
 // All loads/stores are 128-bit and coalesced along the channel axis; statistics are fp32 (GroupNorm partials
 // are combined in fp64) and the reductions are deterministic (no float atomics to global memory).
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -196,14 +197,13 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
 // ---------------------------------------------------------------------------------------------------------------
 // Single-pass GroupNorm(+SiLU): one read of x, one write of y, one launch.
 // Each CTA keeps its pixel chunk of one image in shared memory between the statistics pass and the normalisation
-// pass; the per-chunk partial sums of an image are combined through global memory by ALL CTAs of that image, which
-// therefore have to be co-resident: the host launches this kernel only when chunks * B <= SMs * (CTAs per SM that
-// the occupancy calculator grants for this much shared memory), otherwise the two-kernel path above runs.
-// Arrival / departure counters live in a zero-initialised device array and are reset by the last departing CTA of
-// an image, so every launch (and every CUDA-graph replay) starts from zero. pdl_wait() precedes every global access,
-// which also serialises consecutive launches on the counters.
-__device__ unsigned int g_gn_counters[2 * 1024];
-
+// pass; the per-chunk partial sums are exchanged through the caller's workspace across ONE grid-wide barrier. The
+// kernel is launched COOPERATIVELY (launch_k_coop): the driver guarantees that all CTAs are resident together or
+// refuses the launch, and the barrier is cooperative_groups' grid sync, whose state belongs to the launch — no
+// library-global counters, so launches on different streams (or from different CUDA graphs) cannot interfere, and
+// there is nothing to reset between CUDA-graph replays. The host picks this path only when chunks * B fits
+// (occupancy calculator, gn_fused_plan); otherwise the two-kernel path above runs. pdl_wait() precedes every
+// global access.
 __global__ void __launch_bounds__(GN_THREADS)
 gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, float* ws) {
@@ -284,22 +284,10 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
     float* o = ws + (static_cast<long long>(b) * chunks + chunk) * 64;
     __stcg(o + g, s);
     __stcg(o + 32 + g, q);
-    // ---- publish, then wait until every chunk of this image has published (all of them are resident)
-    __threadfence();
-    __syncwarp();
-    if (g == 0) {
-      atomicAdd(&g_gn_counters[2 * b], 1u);
-      volatile unsigned int* arrive = &g_gn_counters[2 * b];
-      unsigned int spins = 0;
-      while (*arrive < static_cast<unsigned int>(chunks)) {
-        __nanosleep(32);
-        if (++spins > (1u << 27)) asm volatile("trap;");   // > 4 s: co-residency was violated; fail loudly, do not hang
-      }
-      __threadfence();
-    }
-    __syncwarp();
   }
-  __syncthreads();
+  // ---- publish, then wait until every chunk has published: grid-wide barrier of the cooperative launch
+  __threadfence();
+  cooperative_groups::this_grid().sync();
   pdl_launch_dependents();
   // ---- finalize the statistics (every CTA of the image does this redundantly: 8 lanes per group, fp64, fixed order)
   if (threadIdx.x < 256) {
@@ -325,17 +313,7 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
     }
   }
   __syncthreads();
-  // the partials of this image may be overwritten (next launch) only after every CTA has read them: the last CTA
-  // to depart resets both counters
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int d = atomicAdd(&g_gn_counters[2 * b + 1], 1u);
-    if (d == static_cast<unsigned int>(chunks) - 1) {
-      g_gn_counters[2 * b + 1] = 0u;
-      __threadfence();
-      g_gn_counters[2 * b] = 0u;
-    }
-  }
+  // (the partials in `ws` are overwritten by the NEXT GroupNorm launch only: stream order / pdl_wait() there)
   if (!active) return;
   // ---- pass 2: shared -> normalise (+SiLU) -> global
   float a[8], sft[8];
@@ -508,9 +486,11 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   int fc = 0;
   size_t fsmem = 0;
   if (gn_fused_plan(B, HW, C, &fc, &fsmem)) {
-    launch_k(gn_fused_kernel, dim3(fc, B), dim3(GN_THREADS), fsmem, st, src, reinterpret_cast<__half*>(y), HW, cpg, fc,
-             eps, gamma, beta, apply_silu, stats_ws);
-    return check_launch("gn_fused");
+    const cudaError_t e = launch_k_coop(gn_fused_kernel, dim3(fc, B), dim3(GN_THREADS), fsmem, st, src,
+                                        reinterpret_cast<__half*>(y), HW, cpg, fc, eps, gamma, beta, apply_silu, stats_ws);
+    if (e == cudaSuccess) return check_launch("gn_fused");
+    if (e != cudaErrorCooperativeLaunchTooLarge) return set_error(std::string("gn_fused launch: ") + cudaGetErrorString(e));
+    cudaGetLastError();   // the driver could not co-schedule the grid (e.g. a partitioned device): two-kernel path
   }
   // stats chunks index the caller's workspace ([B][chunks][2][32] floats, contract: B * 4096 floats): never more
   // than GN_MAX_CHUNKS per image

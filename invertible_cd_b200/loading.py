@@ -21,6 +21,7 @@ import torch
 from . import arch
 from .schedulers import DDIMScheduler, DDPMScheduler
 from .unet import B200UNet
+from .vae import B200VAE, VaeImageProcessor, synthetic_vae_state_dict, vae_config
 
 LORA_ALPHA = 8  # utils/loading.py:19-21 (peft default lora_alpha with LoraConfig(r=...))
 
@@ -35,6 +36,7 @@ class ICDPipeline:
         self.tokenizer_2, self.text_encoder_2 = tokenizer_2, text_encoder_2
         self.device, self.dtype = torch.device(device), dtype
         self.vae_scale_factor = 8
+        self.image_processor = VaeImageProcessor()      # .postprocess(...), utils/generation_sdxl.py:468
 
     @property
     def _execution_device(self):
@@ -153,6 +155,27 @@ def _unet_source(model_id, w_embed_dim, is_xl, device="cpu"):
     return cfg, sd, text
 
 
+def _vae_source(model_id, device, is_xl):
+    """-> B200VAE or None. Synthetic models get a random-init AutoencoderKL of the published shape (83.65 M parameters;
+    scaling factor 0.18215 / 0.13025); local diffusers directories load `vae/config.json` + weights when present."""
+    if isinstance(model_id, str) and model_id.startswith("synthetic"):
+        cfg = vae_config(scaling_factor=0.13025 if is_xl else 0.18215, sample_size=1024 if is_xl else 512)
+        return B200VAE(cfg, synthetic_vae_state_dict(cfg, seed=7), device)
+    vdir = os.path.join(model_id, "vae")
+    if not os.path.isdir(vdir):
+        return None
+    with open(os.path.join(vdir, "config.json")) as f:
+        raw = json.load(f)
+    base = vars(vae_config())
+    cfg = vae_config(**{k: (tuple(raw[k]) if isinstance(raw[k], list) else raw[k]) for k in base if k in raw})
+    for fname in ("diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.safetensors",
+                  "diffusion_pytorch_model.bin"):
+        p = os.path.join(vdir, fname)
+        if os.path.exists(p):
+            return B200VAE(cfg, _load_tensor_file(p), device)
+    return None
+
+
 def _validate(cfg, sd):
     shapes = arch.unet_param_shapes(cfg)
     missing = [k for k in shapes if k not in sd]
@@ -195,8 +218,8 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
     text_encoder = text.get("text_encoder")
     if text_encoder is not None:
         text_encoder = text_encoder.to(device)
-    ldm_stable = ICDPipeline(B200UNet(cfg, sd, device), scheduler, None, text.get("tokenizer"), text_encoder,
-                             device, tdtype)
+    ldm_stable = ICDPipeline(B200UNet(cfg, sd, device), scheduler, _vae_source(model_id, device, False),
+                             text.get("tokenizer"), text_encoder, device, tdtype)
     students = []
     for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
         if ckpt is None:
@@ -217,8 +240,8 @@ def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_che
     _validate(cfg, sd)
     scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
     scheduler.num_train_timesteps = 1000
-    stable_pipe = ICDPipeline(B200UNet(cfg, sd, device), scheduler, None, text.get("tokenizer"),
-                              text.get("text_encoder"), device, torch.float16)
+    stable_pipe = ICDPipeline(B200UNet(cfg, sd, device), scheduler, _vae_source(model_id, device, True),
+                              text.get("tokenizer"), text.get("text_encoder"), device, torch.float16)
     pipes = []
     for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
         print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')

@@ -47,9 +47,14 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_debug_sync = __import__("os").environ.get("ICD_DEBUG_SYNC", "0") != "0"
+
+
 def _count(n=1):
     global launch_count
     launch_count += n
+    if _debug_sync:       # debugging aid: surface an asynchronous kernel fault at the op that caused it
+        torch.cuda.synchronize()
 
 
 def _f16(t, name):
@@ -249,11 +254,12 @@ def upsample2x(x, B, H, W, out=None):
     return out
 
 
-def im2col_s2(x, B, H, W, out=None):
+def im2col_s2(x, B, H, W, out=None, pad=1):
+    """Operand of a stride-2 3x3 conv. pad=1: U-Net Downsample2D; pad=0: VAE encoder Downsample2D (zeros bottom/right)."""
     Cc = x.shape[1]
     if out is None:
         out = torch.empty((B * (H // 2) * (W // 2), 9 * Cc), device=x.device, dtype=torch.float16)
-    _lib.check(_lib.load().icd_im2col_s2(_ptr(x), _ptr(out), B, H, W, Cc, _stream()), "icd_im2col_s2")
+    _lib.check(_lib.load().icd_im2col_s2_pad(_ptr(x), _ptr(out), B, H, W, Cc, pad, _stream()), "icd_im2col_s2")
     _count()
     return out
 

@@ -1,7 +1,7 @@
 """Public-API parity on the GPU: load_models / Generator / runner / invert / p2p controllers / SDXL samplers over the
 B200 U-Net vs the same host code over the CPU oracle U-Net (the host code itself is pinned to the reference's output in
-tests/test_host_cpu.py). Tolerance: rel-L2 <= 2e-2 on K-step latents (fp16 noise floor through K U-Net passes;
-measured ~3e-4..2e-3), stated per test."""
+tests/test_host_cpu.py). Tolerance: relative L2 error of the K-step latents <= 2x the value measured on the B200
+(fp16 noise floor through K U-Net passes: 2.4e-4 .. 1.7e-3), stated per test."""
 import os
 import sys
 
@@ -73,7 +73,7 @@ def test_runner_generation_with_attention_store(sd15_models):
                                    dynamic_guidance=True, tau1=0.8, tau2=0.8)[-1]
     err = _rel(lat, ref)
     print("runner 4-step rel-L2:", err)
-    assert err <= 2e-2
+    assert err <= 5e-4                                   # measured 2.41e-4
 
 
 def test_invert_then_edit_with_refine_controller(sd15_models):
@@ -95,7 +95,7 @@ def test_invert_then_edit_with_refine_controller(sd15_models):
     _, o_inv = o_solver.cons_inversion(image_latent, guidance_scale=0.0, w_embed_dim=512, seed=3)
     err_inv = _rel(x_inv, o_inv[0])
     print("inversion rel-L2:", err_inv)
-    assert err_inv <= 2e-2
+    assert err_inv <= 3.2e-3                             # measured 1.57e-3
 
     prompts = ["a photo of a house on a mountain", "a photo of a house on a mountain at winter evening"]
 
@@ -116,7 +116,7 @@ def test_invert_then_edit_with_refine_controller(sd15_models):
     err = _rel(lat, ref)
     print("edit rel-L2:", err, "steps", ctrl.cur_step, o_ctrl.cur_step)
     assert ctrl.cur_step == o_ctrl.cur_step == 4
-    assert err <= 2e-2
+    assert err <= 3.5e-3                                 # measured 1.71e-3
 
 
 def test_cuda_graph_replay_equals_eager(sd15_models):
@@ -180,14 +180,25 @@ def test_sdxl_sample_and_inverse(sd15_models):
                                                   amplify_prompt=src("cpu", torch.float32), **kw)
     err = _rel(got, ref)
     print("sdxl reverse 3-step rel-L2:", err)
-    assert got.dtype == torch.float16 and err <= 2e-2
+    assert got.dtype == torch.float16 and err <= 1e-3    # measured 4.8e-4
     img_lat = torch.randn(B, 4, 16, 16, generator=g) * 0.3
     kwi = dict(num_inference_steps=3, timesteps=[19, 339, 699], guidance_scale=0.0, is_sdxl=True, seed=4)
-    goti = generation_sdxl.inverse_sample_deterministic(fpipe, img_lat.cuda(), emb("cuda", torch.float16), **kwi)
-    refi = generation_sdxl.inverse_sample_deterministic(o_fpipe, img_lat, emb("cpu", torch.float32), **kwi)
+    goti, start = generation_sdxl.inverse_sample_deterministic(fpipe, img_lat.cuda(), emb("cuda", torch.float16),
+                                                               return_start_latent=True, **kwi)
+    # the start latent = add_noise(image latent, noise at t=19) with the noise drawn IN THE PIPELINE DTYPE on the CPU
+    # generator, as diffusers' prepare_latents / randn_tensor do (fp16 here; an fp32 draw gives other values)
+    noise = torch.randn(img_lat.shape, generator=torch.Generator().manual_seed(4), dtype=torch.float16)
+    exp_start = fpipe.scheduler.add_noise(img_lat.half(), noise, torch.tensor([19]))
+    torch.testing.assert_close(start.cpu().float(), exp_start.float(), atol=2e-3, rtol=2e-3)
+    # the oracle pipeline is fp32 and would draw fp32 noise: run its loop from the same start latent instead
+    e = emb("cpu", torch.float32)
+    al, sg = generation_sdxl._schedule_tables(o_fpipe, "cpu")
+    refi = generation_sdxl._loop(o_fpipe, start.float().cpu(), [19, 339, 699], [339, 699, 999], e["prompt_embeds"], None,
+                                 {k: e[k] for k in ("text_embeds", "time_ids")}, [0.0] * B, False, 0.0, 0.0,
+                                 torch.float32, al, sg)
     erri = _rel(goti, refi)
     print("sdxl forward 3-step rel-L2:", erri)
-    assert erri <= 2e-2
+    assert erri <= 3.5e-3                                # measured 1.74e-3
 
 
 def test_library_graph_cache_equals_eager(sd15_models):

@@ -507,3 +507,39 @@ def test_executor_packs_all_cross_attention_kv_projections_into_one_matrix():
         assert len(hits) == 1, prefix
         seen += 1
     assert seen == len(blocks)
+
+
+# ---------------------------------------------------------------------------------------------- VAE
+def test_vae_oracle_param_count_and_key_inventory():
+    """Pins for the AutoencoderKL restatement: the public parameter count of the SD VAE (83,653,863; encoder
+    34,163,592, decoder 49,490,179) and the product's key/shape inventory == the oracle's state dict."""
+    from invertible_cd_b200.vae import vae_config, vae_param_shapes
+    from oracle import vae_oracle as V
+    with torch.device("meta"):
+        m = V.AutoencoderKL(V.sd15_vae_config())
+    assert sum(p.numel() for p in m.parameters()) == 83_653_863
+    assert sum(p.numel() for p in m.encoder.parameters()) == 34_163_592
+    assert sum(p.numel() for p in m.decoder.parameters()) == 49_490_179
+    shapes = vae_param_shapes(vae_config())
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v) for k, v in shapes.items()}
+    assert V.sdxl_vae_config().scaling_factor == 0.13025 and V.sd15_vae_config().scaling_factor == 0.18215
+
+
+def test_vae_oracle_small_roundtrip_shapes_and_distribution():
+    from invertible_cd_b200.vae import DiagonalGaussianDistribution, VaeImageProcessor
+    from oracle import vae_oracle as V
+    torch.manual_seed(0)
+    m = V.AutoencoderKL(V.VAEConfig(block_out_channels=(32, 32, 64, 64))).eval()
+    x = torch.rand(2, 3, 64, 64) * 2 - 1
+    with torch.no_grad():
+        dist = m.encode(x).latent_dist
+        img = m.decode(dist.mean, return_dict=False)[0]
+    assert dist.mean.shape == (2, 4, 8, 8) and img.shape == (2, 3, 64, 64)
+    mine = DiagonalGaussianDistribution(dist.parameters)
+    a = mine.sample(torch.Generator().manual_seed(3))
+    b = dist.sample(torch.Generator().manual_seed(3))
+    assert torch.equal(a, b) and torch.equal(mine.mode(), dist.mode())
+    pil = VaeImageProcessor.postprocess(img, output_type="pil", do_denormalize=[True, True])
+    assert len(pil) == 2 and pil[0].size == (64, 64)
+    arr = VaeImageProcessor.postprocess(img, output_type="np")
+    assert arr.shape == (2, 64, 64, 3) and arr.min() >= 0.0 and arr.max() <= 1.0

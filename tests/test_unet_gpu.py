@@ -4,7 +4,8 @@ the diffusers U-Net, same weights / latents / context / timestep / w-embedding.
 Tolerance. north_star asks rtol=1e-3/atol=1e-4 "fp16" against the reference U-Net. The kernels store fp16
 activations between ~100 layers (fp32 accumulation inside each), so — exactly like the reference's own fp16 mode —
 the output carries accumulated fp16 rounding noise; the gate used here is therefore
-  (1) max |err| <= 2e-2 * max|ref| and relative L2 error <= 5e-3 against the fp32 oracle, and
+  (1) max |err| <= 3e-3 * max|ref| and relative L2 error <= 2.2e-3 against the fp32 oracle (measured on B200:
+      8.3e-4..1.4e-3 and 8.0e-4..1.1e-3; the gate is 2x that), and
   (2) the error is no larger than 1.5x that of the oracle itself run in fp16 on the GPU (PyTorch eager; checker
       only) against the same fp32 oracle — i.e. we are at the fp16 noise floor of the reference's own arithmetic.
 """
@@ -72,8 +73,8 @@ def test_forward_matches_oracle(cfg_name, rows, t):
     emax, el2 = _err(out, ref)
     fmax, fl2 = _err(ref16, ref)
     print(f"{cfg_name} rows={rows} t={t}: ours max {emax:.3e} l2 {el2:.3e} | torch-fp16 max {fmax:.3e} l2 {fl2:.3e}")
-    assert emax <= 2e-2 and el2 <= 5e-3, (emax, el2)
-    assert el2 <= 1.5 * fl2 + 1e-4, (el2, fl2)
+    assert emax <= 3e-3 and el2 <= 2.2e-3, (emax, el2)
+    assert el2 <= 1.1 * fl2, (el2, fl2)      # measured 0.62..0.67 of PyTorch-eager fp16's error
 
 
 def test_fused_update_matches_predicted_origin():
@@ -118,7 +119,8 @@ def test_controller_protocol_and_store_layout():
     with torch.no_grad():
         ref = oracle(lat, torch.tensor(779), encoder_hidden_states=ctx, timestep_cond=w)["sample"]
     emax, el2 = _err(out, ref)
-    assert el2 <= 5e-3, (emax, el2)
+    print("store forward:", emax, el2)
+    assert el2 <= 2.2e-3, (emax, el2)
     got, exp = store.attention_store, ref_store.attention_store
     assert set(got) == set(exp)
     for key in exp:
@@ -177,7 +179,7 @@ def test_edit_controller_matches_oracle():
         ref = oracle(lat, torch.tensor(999), encoder_hidden_states=ctx, timestep_cond=w)["sample"]
     emax, el2 = _err(out, ref)
     print("edit:", emax, el2)
-    assert el2 <= 6e-3, (emax, el2)
+    assert el2 <= 2.2e-3 and emax <= 3.6e-3, (emax, el2)      # measured 1.08e-3 / 1.79e-3
     assert ctrl.cur_step == 1 and ref_ctrl.cur_step == 1
 
 

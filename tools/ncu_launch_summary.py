@@ -29,7 +29,7 @@ def main(csv_path, shapes_path, top=40):
     total = sum(ns for _, ns in rows)
     fam = defaultdict(lambda: [0, 0.0, 0.0])
     for (name, ns), db in zip(rows, dram):
-        key = name.split("<")[0].split("(")[0]
+        key = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "").split("<")[0].split("(")[0]
         key = key.replace("void ", "").replace("icd::", "")
         if "at::native" in name or "at_cuda" in name:
             key = "torch:" + key[:50]
