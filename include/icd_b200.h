@@ -82,6 +82,11 @@ typedef struct IcdGemm {
   const float* upd_x;
   float* upd_out;
   float alpha_t, sigma_t, alpha_s, sigma_s;
+  /* softmax-from-statistics epilogue (fp16 row-major output only): out = exp2(alpha*acc - s[0]) * s[1] with
+   * s = exp_stats[(z*M + row)*2 ..] — the (scaled reference maximum, 1 / row sum) pairs icd_attention_ex wrote.
+   * Materialises normalised attention probabilities (AttentionStore capture of self-attention maps,
+   * utils/p2p.py:145-149) in ONE pass over the scores, without a separate softmax kernel. NULL = off. */
+  const float* exp_stats;
 } IcdGemm;
 
 int icd_gemm(const IcdGemm* g, void* stream);
@@ -97,6 +102,11 @@ int icd_gemm_pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_b
 int icd_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk, int D,
                   long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale, void* probs_out,
                   long long probs_ld, void* stream);
+/* Same, plus stats_out (optional): fp32 [B*H][Nq][2] = (reference maximum * scale * log2(e), 1 / row sum) of the
+ * online softmax, for any N_kv: icd_gemm's exp_stats epilogue turns Q.K^T into the normalised probabilities with them. */
+int icd_attention_ex(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk, int D,
+                     long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale, void* probs_out,
+                     long long probs_ld, float* stats_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Memory-bound kernels (HBM roofline): normalisations, activations, layout, embeddings, update.

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libicd_b200.so")
 
 # every symbol include/icd_b200.h declares (tests assert the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "icd_last_error", "icd_device_info", "icd_abi_version", "icd_set_pdl", "icd_gemm", "icd_gemm_pick_bn", "icd_attention",
+    "icd_last_error", "icd_device_info", "icd_abi_version", "icd_set_pdl", "icd_gemm", "icd_gemm_pick_bn", "icd_attention", "icd_attention_ex",
     "icd_groupnorm", "icd_groupnorm_launches", "icd_layernorm", "icd_softmax", "icd_upsample2x", "icd_im2col_s2", "icd_im2col_s2_pad", "icd_latent_to_nhwc",
     "icd_timestep_embedding", "icd_guidance_embedding", "icd_silu", "icd_add", "icd_consistency_update",
 ]
@@ -33,6 +33,7 @@ class IcdGemm(C.Structure):
         ("ws", C.c_void_p), ("ws_bytes", C.c_longlong),
         ("upd_x", C.c_void_p), ("upd_out", C.c_void_p),
         ("alpha_t", C.c_float), ("sigma_t", C.c_float), ("alpha_s", C.c_float), ("sigma_s", C.c_float),
+        ("exp_stats", C.c_void_p),
     ]
 
 
@@ -58,6 +59,9 @@ def load():
     lib.icd_gemm_pick_bn.argtypes = [C.c_int] * 6
     lib.icd_attention.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_longlong] * 4 + [C.c_float, C.c_void_p,
                                                                                          C.c_longlong, C.c_void_p]
+    lib.icd_attention_ex.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_longlong] * 4 + [C.c_float, C.c_void_p,
+                                                                                            C.c_longlong, C.c_void_p,
+                                                                                            C.c_void_p]
     lib.icd_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.icd_groupnorm_launches.argtypes = [C.c_int] * 3

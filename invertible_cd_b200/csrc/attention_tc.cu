@@ -42,6 +42,7 @@ struct AttnParams {
   long long out_ld;
   __half* probs;      // optional [B*H][Nq][probs_ld]
   long long probs_ld;
+  float* stats;       // optional [B*H][Nq][2]: (m_run * scale_log2e, 1 / l) of the online softmax
 #ifdef ICD_ATTN_PROFILE
   long long* prof;    // [MT][8] phase cycle counters of one softmax warp per query tile (debug builds only)
 #endif
@@ -397,6 +398,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld_wait();
       inv = 1.f / l16[0];
     }
+    if (p.stats != nullptr && q < p.Nq)
+      *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(bh) * p.Nq + q) * 2) =
+          make_float2(m_run * p.scale_log2e, inv);
     if (p.probs != nullptr && n_kv <= 2) {
       // <= 128 keys: emit the normalised probabilities (AttentionStore capture). The un-normalised P tiles are still
       // in tensor memory (nothing overwrote S0/S1). They are staged through the idle K/V ring in a swizzled row
@@ -531,6 +535,13 @@ extern "C" void icd_attention_prof_dump(int n_kv) {
 extern "C" int icd_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
                              int D, long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale,
                              void* probs_out, long long probs_ld, void* stream) {
+  return icd_attention_ex(q, k, v, out, B, H, Nq, Nk, D, q_ld, k_ld, v_ld, out_ld, scale, probs_out, probs_ld, nullptr,
+                          stream);
+}
+
+extern "C" int icd_attention_ex(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
+                                int D, long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale,
+                                void* probs_out, long long probs_ld, float* stats_out, void* stream) {
   if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return set_error("icd_attention: null operand");
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return set_error("icd_attention: empty problem");
   if (probs_out != nullptr && Nk > 128)
@@ -559,6 +570,7 @@ extern "C" int icd_attention(const void* q, const void* k, const void* v, void* 
   p.out_ld = out_ld;
   p.probs = reinterpret_cast<__half*>(probs_out);
   p.probs_ld = probs_ld;
+  p.stats = stats_out;
 #ifdef ICD_ATTN_PROFILE
   static long long* prof_buf = nullptr;
   if (prof_buf == nullptr) cudaMallocManaged(&prof_buf, 16 * sizeof(long long));

@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA descriptor construction (cached), tile-width heuristic, launch.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -251,7 +252,8 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   const int fbm = g->force_bm;
   // split-K (fp32 partials in the caller's workspace + a reduce kernel) for few-tile, deep-K problems
   const bool split_ok = g->ws != nullptr && !g->geglu && !g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR &&
-                        g->Z == 1 && (g->N % 16) == 0 && g->upd_x == nullptr && (g->ldc % 8) == 0 &&
+                        g->Z == 1 && (g->N % 16) == 0 && g->upd_x == nullptr && g->exp_stats == nullptr &&
+                        (g->ldc % 8) == 0 &&
                         (g->residual == nullptr || (g->ldr % 8) == 0);
   int max_splits = 1;
   if (split_ok) {
@@ -385,6 +387,7 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   p.alpha_t = g->alpha_t; p.sigma_t = g->sigma_t; p.alpha_s = g->alpha_s; p.sigma_s = g->sigma_s;
   if (p.upd_x != nullptr && !(p.out_fp32 && p.out_mode == GEMM_OUT_TRANSPOSED))
     return set_error("icd_gemm: fused update needs fp32 transposed output");
+  p.exp_stats = reinterpret_cast<const float2*>(g->exp_stats);
 
   p.kb_per_split = p.num_kb;   // single split: the whole K range (num_kb is final here)
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -434,10 +437,22 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   const int n_out_chk = g->geglu ? g->N / 2 : g->N;
   p.epi_tma = (!g->out_fp32 && g->out_mode == GEMM_OUT_ROWMAJOR && aligned && res_ok && (n_out_chk % 8) == 0) ? 1 : 0;
   if (g->geglu && !p.epi_tma) return set_error("icd_gemm: GEGLU needs an aligned fp16 row-major output");
+  if (g->exp_stats != nullptr && (!p.epi_tma || g->geglu || g->residual != nullptr))
+    return set_error("icd_gemm: exp_stats needs a plain aligned fp16 row-major output (N % 8 == 0, no residual)");
+  // per-warp epilogue (EPI_WARP / EPI_WARP_RES): every epilogue warp stages and stores its own 32x32 block
+  static const bool warp_epi_enabled = [] { const char* e = getenv("ICD_GEMM_WARP_EPI"); return e == nullptr || atoi(e) != 0; }();
+  // Large plain / GEGLU linears: one 256x256 tile per CTA pair (tcgen05.mma.cta_group::2, gemm2sm_tc.cu) where the
+  // measurements say it beats the single-CTA kernel
+  const bool use_2sm = p.epi_tma && g->a_mode == GEMM_A_TILED && g->a1 == nullptr && g->Z == 1 && !g->b_mn_major &&
+                       g->residual == nullptr && g->rowvec == nullptr && g->alpha == 1.0f && g->exp_stats == nullptr &&
+                       g->force_bm == 0 && g->force_splits == 0 && (g->force_bn == 0 || g->force_bn == 256) &&
+                       g->a_z1_stride == 0 && g->a_z2_stride == 0 && g->b_z1_stride == 0 && g->b_z2_stride == 0 &&
+                       gemm2sm_wanted(g->M, g->N, g->K0, g->geglu != 0);
+  const bool warp_epi = warp_epi_enabled && p.epi_tma && !g->geglu && !use_2sm;
   if (p.epi_tma) {
     const uint64_t n_out = (uint64_t)(g->geglu ? g->N / 2 : g->N);
     const uint64_t z2 = (uint64_t)((g->Z + p.ZA1 - 1) / p.ZA1);
-    const uint32_t box[4] = {32, 128, 1, 1};
+    const uint32_t box[4] = {32, warp_epi ? 32u : 128u, 1, 1};
     const uint64_t dims[4] = {n_out, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
     const uint64_t s1 = g->out_z1_stride > 0 ? (uint64_t)g->out_z1_stride * 2 : (uint64_t)g->ldc * 2;
     const uint64_t s2 = g->out_z2_stride > 0 ? (uint64_t)g->out_z2_stride * 2 : s1;
@@ -451,12 +466,7 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     }
   }
 
-  // Large plain / GEGLU linears: one 256x256 tile per CTA pair (tcgen05.mma.cta_group::2, gemm2sm_tc.cu) where the
-  // measurements say it beats the single-CTA kernel
-  if (p.epi_tma && g->a_mode == GEMM_A_TILED && g->a1 == nullptr && g->Z == 1 && !g->b_mn_major &&
-      g->residual == nullptr && g->rowvec == nullptr && g->alpha == 1.0f && g->force_bm == 0 && g->force_splits == 0 &&
-      (g->force_bn == 0 || g->force_bn == 256) && g->a_z1_stride == 0 && g->a_z2_stride == 0 &&
-      g->b_z1_stride == 0 && g->b_z2_stride == 0 && gemm2sm_wanted(g->M, g->N, g->K0, g->geglu != 0)) {
+  if (use_2sm) {
     CUtensorMap tmB2;
     const uint64_t dims[4] = {(uint64_t)g->K0, (uint64_t)g->N, 1, 1};
     const uint64_t str[3] = {(uint64_t)g->b_ld * 2, (uint64_t)g->b_ld * 2, (uint64_t)g->b_ld * 2};
@@ -484,6 +494,14 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     if (bn == 128) ICD_LAUNCH(128, 128, EPI_STAGED_GEGLU);
     if (bn == 256) ICD_LAUNCH(128, 256, EPI_STAGED_GEGLU);
     return set_error("icd_gemm: GEGLU supports BN 128 / 256");
+  }
+  if (warp_epi) {
+    if (p.res_tma) {
+      if (bm == 256) { ICD_LAUNCH_BN(256, EPI_WARP_RES) }
+      ICD_LAUNCH_BN(128, EPI_WARP_RES)
+    }
+    if (bm == 256) { ICD_LAUNCH_BN(256, EPI_WARP) }
+    ICD_LAUNCH_BN(128, EPI_WARP)
   }
   // short main loops cannot hide the row-per-thread residual reads: stream the residual through TMA + smem
   if (p.epi_tma && p.res_tma && p.num_kb <= 24) {

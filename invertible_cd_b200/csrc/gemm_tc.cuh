@@ -61,9 +61,12 @@ struct GemmParams {
   const float* upd_x;     // current latent x_t (fp32, NCHW) or null
   float* upd_out;         // next latent x_s (fp32, NCHW)
   float alpha_t, sigma_t, alpha_s, sigma_s;
+  // softmax-from-statistics (staged fp16 epilogue): out = exp2(alpha*acc - s.x) * s.y, s = exp_stats[z*M + row]
+  const float2* exp_stats;
 };
 
-enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3, EPI_STAGED_F32 = 4 };
+enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3, EPI_STAGED_F32 = 4,
+             EPI_WARP = 5, EPI_WARP_RES = 6 };
 
 template <int BM_, int BN, int EPI>
 struct GemmCfg {
@@ -73,14 +76,16 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int C_BYTES = 4 * 8192;  // epilogue staging: 4 atoms of [128 rows x 32 cols] fp16, 64B swizzle
-  static constexpr int R_BYTES = (EPI == EPI_STAGED_RES) ? 4 * 8192 : 0;  // TMA-loaded residual units (2 x 16 KB)
-  static constexpr int BUDGET = 232448 - 1024 - 256 - C_BYTES - R_BYTES;
+  // TMA-loaded residual: 2 x 16 KB units (EPI_STAGED_RES) or 8 warps x 2 x 2 KB (EPI_WARP_RES)
+  static constexpr int R_BYTES = (EPI == EPI_STAGED_RES || EPI == EPI_WARP_RES) ? 4 * 8192 : 0;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - C_BYTES - R_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int HALF_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per 128-row half
   static constexpr int ACC_COLS = HALVES * HALF_STRIDE;                        // one accumulator set
   static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;             // double-buffer when TMEM allows
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;                      // power of two in [64, 512]
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + R_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + C_BYTES + R_BYTES + 1024 /*align*/ + BAR_BYTES;
   static constexpr int EPI_THREADS = 256;            // 8 epilogue warps: two per TMEM lane quadrant
   static constexpr int THREADS = 64 + EPI_THREADS + ((EPI == EPI_STAGED_RES) ? 32 : 0);  // + residual-producer warp
 };
@@ -107,6 +112,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* res_full = bars + 2 * STAGES + 4;    // [2] residual unit landed in smem_r (TMA tx-count)
   uint64_t* res_empty = bars + 2 * STAGES + 6;   // [2] residual unit consumed by the 128 epilogue threads
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  uint64_t* wres_bar = bars + 2 * STAGES + 9;    // [8 warps][2] per-warp residual sub-tile landed (EPI_WARP_RES)
+  static_assert((2 * 8 + 9 + 16) * 8 <= Cfg::BAR_BYTES, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(&res_full[i], 1);
       mbar_init(&res_empty[i], Cfg::EPI_THREADS);
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&wres_bar[i], 1);
     tma_prefetch_desc(&tmOut);
     tma_prefetch_desc(&tmRes);
     fence_mbar_init();
@@ -355,6 +363,131 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       if (leader) bulk_wait0();
+    } else if constexpr (EPI == EPI_WARP || EPI == EPI_WARP_RES) {
+      // ---- per-warp staged epilogue: every epilogue warp owns a [32 rows x 32 columns] block of each 64-column unit
+      // (rows = its TMEM lane quadrant, columns = its half of the unit) and runs its own pipeline
+      //   tcgen05.ld -> (+bias / rowvec / residual | softmax-from-stats) -> 64B-swizzled smem block -> TMA store,
+      // double-buffered per warp, with NO CTA-wide barrier: the only shared event is the release of the accumulator.
+      // The residual block is fetched by the warp's own TMA load one step ahead (the first one of a tile before the
+      // accumulator is awaited, i.e. behind the tile's main loop).
+      constexpr bool RES = (EPI == EPI_WARP_RES);
+      constexpr int outw = BN;
+      constexpr int units = (outw + 63) / 64;
+      constexpr int steps = HALVES * units;          // (half, unit) pairs of one tile, in processing order
+      const int ew = warp - 2;                       // 0..7
+      uint8_t* my_out = smem_c + ew * 4096;          // 2 x [32 rows x 64 B]
+      uint8_t* my_res = smem_r + ew * 4096;
+      uint64_t* my_bar = wres_bar + ew * 2;
+      const bool lane0 = lane == 0;
+      const uint32_t sw = (lane >> 1) & 3;           // 64B swizzle: 16B-chunk index ^= (row / 2) % 4
+      const int col_w = part * 32;                   // this warp's column offset inside a 64-column unit
+      uint32_t ocount = 0, rcount = 0;               // staged blocks written / residual blocks consumed by this warp
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int tz = tile % tiles_all_z;
+        const int z = tz / tiles_per_z;
+        const int t = tz - z * tiles_per_z;
+        const int mt = t / n_tiles, nt = t - mt * n_tiles;
+        const int acc = iter % ACC_STAGES;
+        const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
+        const int n_out0 = nt * outw;
+        auto step_active = [&](int s) {            // warp-uniform: does this warp have columns in step s?
+          const int u = s % units;
+          const int c = u * 64 + col_w;
+          return s < steps && c < outw && n_out0 + c < p.N;
+        };
+        auto issue_res = [&](int s, uint32_t rc) {   // lane 0: TMA-load the residual block of step s into buffer rc & 1
+          const int half = s / units, u = s % units;
+          mbar_expect_tx(&my_bar[rc & 1], 2048);
+          tma_load_4d(my_res + (rc & 1) * 2048, &tmRes, &my_bar[rc & 1], n_out0 + u * 64 + col_w,
+                      mt * BM + half * 128 + quad * 32, 0, 0);
+        };
+        int s = 0;
+        while (s < steps && !step_active(s)) ++s;      // first step in which this warp has columns
+        if (RES && lane0 && s < steps) issue_res(s, rcount);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        while (s < steps) {
+          int nx = s + 1;
+          while (nx < steps && !step_active(nx)) ++nx; // next one (BN = 160: the upper column half skips every third unit)
+          const int half = s / units, u = s % units;
+          const int col_t = u * 64 + col_w;
+          const int ncol = n_out0 + col_t;
+          const int row0 = mt * BM + half * 128 + quad * 32;
+          const int row = row0 + lane;
+          if (RES && lane0 && nx < steps) issue_res(nx, rcount + 1);
+          // this warp's staging buffer (ocount & 1) was last used two blocks ago: its TMA store must have read it
+          if (lane0) bulk_wait_read1();
+          __syncwarp();
+          float v[32];
+          tmem_ld32(tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE + (static_cast<uint32_t>(quad * 32) << 16) +
+                        col_t,
+                    v);
+          tmem_ld_wait();
+          const int img = min(row, p.M - 1) / p.rows_per_img;
+          const float* rv = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (ncol + j4 * 4 < p.N) {   // N % 8 == 0 in staged mode: whole groups
+              if (p.bias != nullptr) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + j4);
+              if (rv != nullptr) b1 = __ldg(reinterpret_cast<const float4*>(rv + ncol) + j4);
+            }
+            v[j4 * 4 + 0] = v[j4 * 4 + 0] * p.alpha + (b0.x + b1.x);
+            v[j4 * 4 + 1] = v[j4 * 4 + 1] * p.alpha + (b0.y + b1.y);
+            v[j4 * 4 + 2] = v[j4 * 4 + 2] * p.alpha + (b0.z + b1.z);
+            v[j4 * 4 + 3] = v[j4 * 4 + 3] * p.alpha + (b0.w + b1.w);
+          }
+          if (p.exp_stats != nullptr) {   // warp-uniform
+            float2 est = make_float2(0.f, 0.f);
+            if (row < p.M) est = __ldg(p.exp_stats + static_cast<long long>(z) * p.M + row);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = exp2f(v[j] - est.x) * est.y;
+          }
+          if constexpr (RES) mbar_wait(&my_bar[rcount & 1], (rcount >> 1) & 1);
+          const uint32_t obuf = smem_u32(my_out) + (ocount & 1) * 2048 + lane * 64;
+          const uint32_t rbuf = smem_u32(my_res) + (rcount & 1) * 2048 + lane * 64;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t o[4];
+            if constexpr (RES) {
+              uint4 rr;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w)
+                           : "r"(rbuf + ((cc ^ sw) << 4)));
+              const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[q]));
+                const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q] + f.x, v[cc * 8 + 2 * q + 1] + f.y);
+                o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q], v[cc * 8 + 2 * q + 1]);
+                o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obuf + ((cc ^ sw) << 4)), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3])
+                         : "memory");
+          }
+          if constexpr (RES) ++rcount;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane0) {
+            tma_store_4d(&tmOut, my_out + (ocount & 1) * 2048, ncol, row0, z % p.ZA1, z / p.ZA1);
+            bulk_commit();
+          }
+          ++ocount;
+          s = nx;
+        }
+        // every TMEM read of this accumulator by this thread is complete (tmem_ld_wait above)
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+      }
+      if (lane0) bulk_wait0();
     } else if constexpr (EPI != EPI_DIRECT) {
       // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual | GEGLU) -> swizzled smem -> TMA store.
       // Output is produced in 64-column units through a double-buffered staging area (2 x [128 rows x 64 cols],
@@ -402,6 +535,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 (static_cast<uint32_t>(quad * 32) << 16);
         const int img = min(row, p.M - 1) / p.rows_per_img;
         const float* rv = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
+        float2 est = make_float2(0.f, 0.f);
+        if (p.exp_stats != nullptr && row_ok) est = __ldg(p.exp_stats + static_cast<long long>(z) * p.M + row);
 #pragma unroll 1
         for (int u = 0; u < units; ++u, ++unit) {
           const int unit_cols = min(64, outw - u * 64);
@@ -462,6 +597,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   v[j4 * 4 + 1] = v[j4 * 4 + 1] * p.alpha + (b0.y + b1.y);
                   v[j4 * 4 + 2] = v[j4 * 4 + 2] * p.alpha + (b0.z + b1.z);
                   v[j4 * 4 + 3] = v[j4 * 4 + 3] * p.alpha + (b0.w + b1.w);
+                }
+                if (p.exp_stats != nullptr) {   // warp-uniform
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = exp2f(v[j] - est.x) * est.y;
                 }
                 const uint32_t atom = buf + h32 * 8192 + row_in_tile * 64;
 #pragma unroll

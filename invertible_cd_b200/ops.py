@@ -53,8 +53,8 @@ _debug_sync = __import__("os").environ.get("ICD_DEBUG_SYNC", "0") != "0"
 def _count(n=1):
     global launch_count
     launch_count += n
-    if _debug_sync:       # debugging aid: surface an asynchronous kernel fault at the op that caused it
-        torch.cuda.synchronize()
+    if _debug_sync and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.synchronize()      # debugging aid: surface an asynchronous kernel fault at the op that caused it
 
 
 def _f16(t, name):
@@ -178,8 +178,21 @@ def attn_pv(probs, v, B, H, Nq, Nk, D, out):
     return out
 
 
-def attention(q, k, v, B, H, Nq, Nk, D, scale, out=None, probs_out=None):
-    """Fused attention core. q: [B*Nq, H*D]; k, v: [B*Nk, H*D] (row strides allowed); out: [B*Nq, H*D]."""
+def attn_probs_from_stats(q, k, B, H, Nq, Nk, D, scale, stats, out):
+    """Normalised attention probabilities in one pass over the scores: out[b*H+h, q, :] =
+    exp2(scale*log2(e) * Q.K^T - stats[.., 0]) * stats[.., 1] with the online-softmax statistics `attention(...,
+    stats_out=stats)` produced (AttentionStore capture of self-attention maps, utils/p2p.py:145-149, without a separate
+    softmax pass). out: fp16 [B*H, Nq, Nk], Nk % 8 == 0."""
+    gemm_raw(a0=q, a_mode=0, K0=D, a0_ld=q.stride(0), a_z1_stride=D, a_z2_stride=Nq * q.stride(0), ZA1=H,
+             b=k, b_ld=k.stride(0), b_z1_stride=D, b_z2_stride=Nk * k.stride(0), ZB1=H, M=Nq, N=Nk, K=D, Z=B * H,
+             alpha=scale * 1.4426950408889634, out=out, ldc=out.stride(1), out_z1_stride=out.stride(0),
+             out_z2_stride=H * out.stride(0), out_fp32=0, out_mode=0, exp_stats=stats)
+    return out
+
+
+def attention(q, k, v, B, H, Nq, Nk, D, scale, out=None, probs_out=None, stats_out=None):
+    """Fused attention core. q: [B*Nq, H*D]; k, v: [B*Nk, H*D] (row strides allowed); out: [B*Nq, H*D].
+    `stats_out`: optional fp32 [B*H, Nq, 2] receiving (reference max * scale * log2 e, 1 / row sum) per query row."""
     _f16(q, "q"); _f16(k, "k"); _f16(v, "v")
     if out is None:
         out = torch.empty((B * Nq, H * D), device=q.device, dtype=torch.float16)
@@ -187,9 +200,10 @@ def attention(q, k, v, B, H, Nq, Nk, D, scale, out=None, probs_out=None):
         shape_log.append({"kind": "attention_tc", "B": B, "H": H, "Nq": Nq, "Nk": Nk, "D": D,
                           "probs": probs_out is not None, "flops": 4.0 * B * H * Nq * Nk * D})
     ev = _prof_begin()
-    _lib.check(_lib.load().icd_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Nq, Nk, D, q.stride(0),
-                                         k.stride(0), v.stride(0), out.stride(0), float(scale), _ptr(probs_out),
-                                         probs_out.stride(1) if probs_out is not None else 0, _stream()),
+    _lib.check(_lib.load().icd_attention_ex(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Nq, Nk, D, q.stride(0),
+                                            k.stride(0), v.stride(0), out.stride(0), float(scale), _ptr(probs_out),
+                                            probs_out.stride(1) if probs_out is not None else 0, _ptr(stats_out),
+                                            _stream()),
                "icd_attention")
     _count()
     _work("attention", 4.0 * B * H * Nq * Nk * D)

@@ -269,6 +269,15 @@ class B200UNet:
             out = ops.attention(q, k, v, B, heads, Nq, Nk, d, scale, probs_out=probs)
             ctrl.call_rows(probs[..., :Nk], is_cross, place, self._cond_only)
             return out
+        if req == "read" and Nk % 8 == 0:
+            # larger read-only maps (self-attention, N_q <= 1024): the fused kernel produces the output and the
+            # online-softmax statistics; one more pass over Q.K^T writes the normalised probabilities directly
+            stats = torch.empty((B * heads, Nq, 2), device=q.device, dtype=torch.float32)
+            out = ops.attention(q, k, v, B, heads, Nq, Nk, d, scale, stats_out=stats)
+            probs = torch.empty((B * heads, Nq, Nk), device=q.device, dtype=torch.float16)
+            ops.attn_probs_from_stats(q, k, B, heads, Nq, Nk, d, scale, stats, probs)
+            ctrl.call_rows(probs, is_cross, place, self._cond_only)
+            return out
         # explicit probabilities: scores GEMM -> softmax -> controller (may edit in place) -> P.V GEMM
         probs = torch.zeros((B * heads, Nq, ldp), device=q.device, dtype=torch.float16)
         ops.attn_scores(q, k, B, heads, Nq, Nk, d, scale, probs)

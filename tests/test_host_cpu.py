@@ -458,7 +458,7 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.icd_abi_version() == 1
     import ctypes
-    assert ctypes.sizeof(_lib.IcdGemm) == 304
+    assert ctypes.sizeof(_lib.IcdGemm) == 312
 
 
 def test_product_fails_loudly_without_the_extension(monkeypatch):

@@ -391,6 +391,28 @@ def test_attention_fused_self(ops, B, H, Nq, Nk, D):
     _close(out, ref_o, rtol=2e-3, atol=2e-3, what=f"fused attn {Nq}x{Nk} d{D}")
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk,D,peaky", [(2, 8, 1024, 1024, 80, False), (2, 8, 256, 256, 160, False),
+                                               (1, 8, 64, 64, 160, False), (2, 10, 1024, 1024, 64, True),
+                                               (3, 8, 200, 136, 40, True)])
+def test_attention_stats_and_probs_from_stats(ops, B, H, Nq, Nk, D, peaky):
+    """Read-only capture of larger maps (self-attention, N_q <= 1024; utils/p2p.py:145-149): the fused kernel also writes
+    its online-softmax statistics, and one GEMM pass over Q.K^T with the softmax-from-statistics epilogue emits the
+    normalised probabilities. `peaky`: scores with a large spread, so the lazily-updated reference maximum moves."""
+    q, k, v = _rand(B * Nq, H * D, seed=70), _rand(B * Nk, H * D, seed=71), _rand(B * Nk, H * D, seed=72)
+    if peaky:
+        q = (q.float() * 6).half()
+    scale = D ** -0.5
+    stats = torch.full((B * H, Nq, 2), float("nan"), device="cuda")
+    out = ops.attention(q, k, v, B, H, Nq, Nk, D, scale, stats_out=stats)
+    probs = torch.empty((B * H, Nq, Nk), device="cuda", dtype=torch.float16)
+    ops.attn_probs_from_stats(q, k, B, H, Nq, Nk, D, scale, stats, probs)
+    ref_o, ref_p = _attn_ref(q, k, v, B, H, Nq, Nk, D, scale)
+    assert torch.isfinite(stats).all()
+    _close(out, ref_o, rtol=2e-3, atol=2e-3, what="fused attn with stats")
+    _close(probs, ref_p, rtol=4e-3, atol=2e-4, what="probs from stats")
+    torch.testing.assert_close(probs.float().sum(-1), torch.ones(B * H, Nq, device="cuda"), rtol=0, atol=4e-3)
+
+
 @pytest.mark.parametrize("B,H,Nq,D", [(2, 8, 1024, 80), (2, 8, 4096, 40), (1, 20, 1024, 64), (2, 8, 64, 160)])
 def test_attention_fused_cross_with_capture(ops, B, H, Nq, D):
     Nk = 77
