@@ -128,6 +128,9 @@ int icd_layernorm(const void* x, void* y, int rows, int C, float eps, const floa
                   void* stream);
 /* In-place row softmax over [rows][ld] fp16 (first `cols` entries of each row); fp32 statistics. */
 int icd_softmax(void* x, long long rows, int cols, long long ld, void* stream);
+/* Same with a causal mask: row r is query (r % causal_period) of its sequence and sees keys 0..(r % causal_period);
+ * the masked tail is written as zeros (CLIP text transformer, transformers' CLIPAttention causal_attention_mask). */
+int icd_softmax_causal(void* x, long long rows, int cols, long long ld, int causal_period, void* stream);
 /* nearest-neighbour 2x upsample NHWC fp16 (Upsample2D interpolate). */
 int icd_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* gather for the stride-2 3x3 Downsample2D conv: y[B*Ho*Wo][9*C] from NHWC x (pad 1). */
@@ -144,6 +147,12 @@ int icd_timestep_embedding(const float* t, const float* freqs, void* y, int n, i
 /* guidance_scale_embedding (utils/generation.py:96-122): [n] fp32 w -> [n][dim] fp16 = [sin | cos] of (1000 w) f_i */
 int icd_guidance_embedding(const float* w, const float* freqs, void* y, int n, int dim, void* stream);
 /* y = silu(x) elementwise fp16 (time-embedding MLP activations) */
+/* y = act(x) over n fp16 elements (n even): kind 0 SiLU, 1 quick_gelu (x * sigmoid(1.702 x)), 2 exact-erf GELU —
+ * the CLIP text encoders' MLP activations (utils/generation.py:286-303, utils/generation_sdxl.py:9-46 call them). */
+int icd_act(const void* x, void* y, long long n, int kind, void* stream);
+/* CLIPTextEmbeddings: out[r][:] = tok[ids[r]][:] + pos[r % T][:], fp16 [rows][C]; ids int64 on the device. */
+int icd_embed_tokens(const long long* ids, const void* tok, const void* pos, void* out, long long rows, int T, int C,
+                     int vocab, void* stream);
 int icd_silu(const void* x, void* y, long long n, void* stream);
 /* fp16 -> fp16 elementwise add:  y = a + b */
 int icd_add(const void* a, const void* b, void* y, long long n, void* stream);

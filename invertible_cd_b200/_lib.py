@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libicd_b200.so")
 # every symbol include/icd_b200.h declares (tests assert the library exports all of them)
 EXPORTED_SYMBOLS = [
     "icd_last_error", "icd_device_info", "icd_abi_version", "icd_set_pdl", "icd_gemm", "icd_gemm_pick_bn", "icd_attention", "icd_attention_ex",
-    "icd_groupnorm", "icd_groupnorm_launches", "icd_layernorm", "icd_softmax", "icd_upsample2x", "icd_im2col_s2", "icd_im2col_s2_pad", "icd_latent_to_nhwc",
+    "icd_groupnorm", "icd_groupnorm_launches", "icd_layernorm", "icd_softmax", "icd_softmax_causal", "icd_act", "icd_embed_tokens", "icd_upsample2x", "icd_im2col_s2", "icd_im2col_s2_pad", "icd_latent_to_nhwc",
     "icd_timestep_embedding", "icd_guidance_embedding", "icd_silu", "icd_add", "icd_consistency_update",
 ]
 
@@ -68,6 +68,10 @@ def load():
     lib.icd_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_void_p]
     lib.icd_softmax.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_void_p]
+    lib.icd_softmax_causal.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_void_p]
+    lib.icd_act.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    lib.icd_embed_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p]
     lib.icd_upsample2x.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.icd_im2col_s2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.icd_im2col_s2_pad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]

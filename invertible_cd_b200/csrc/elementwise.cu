@@ -111,6 +111,54 @@ __global__ void __launch_bounds__(256) silu_kernel(const __half* __restrict__ x,
   }
 }
 
+// y = act(x): 0 SiLU, 1 quick_gelu (x * sigmoid(1.702 x), CLIP-L), 2 exact-erf GELU (OpenCLIP bigG)
+__global__ void __launch_bounds__(256) act_kernel(const __half2* __restrict__ x, __half2* __restrict__ y, long long n2,
+                                                  int kind) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float2 v = __half22float2(x[i]);
+    float2 r;
+    if (kind == 0) {
+      r = make_float2(v.x / (1.0f + expf(-v.x)), v.y / (1.0f + expf(-v.y)));
+    } else if (kind == 1) {
+      r = make_float2(v.x / (1.0f + expf(-1.702f * v.x)), v.y / (1.0f + expf(-1.702f * v.y)));
+    } else {
+      r = make_float2(0.5f * v.x * (1.0f + erff(v.x * 0.70710678118654752f)),
+                      0.5f * v.y * (1.0f + erff(v.y * 0.70710678118654752f)));
+    }
+    y[i] = __floats2half2_rn(r.x, r.y);
+  }
+}
+
+// out[b*T + t][:] = tok[ids[b*T + t]][:] + pos[t][:]   (CLIPTextEmbeddings), 16-byte vectors
+__global__ void __launch_bounds__(256) embed_tokens_kernel(const long long* __restrict__ ids, const uint4* __restrict__ tok,
+                                                           const uint4* __restrict__ pos, uint4* __restrict__ out,
+                                                           long long rows, int T, int vpr, int vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = rows * vpr;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vpr;
+    const int v = static_cast<int>(i - r * vpr);
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const uint4 a = tok[id * vpr + v], b = pos[static_cast<long long>(r % T) * vpr + v];
+    uint4 o;
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __half22float2(ah[j]), fb = __half22float2(bh[j]);
+      oh[j] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+    }
+    out[i] = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) add_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
                                                   __half* __restrict__ y, long long n) {
   pdl_launch_dependents();
@@ -198,6 +246,22 @@ extern "C" int icd_silu(const void* x, void* y, long long n, void* stream) {
   launch_k(silu_kernel, dim3(grid_for(n)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __half*>(x),
                                                                               reinterpret_cast<__half*>(y), n);
   return check_launch("silu");
+}
+
+extern "C" int icd_act(const void* x, void* y, long long n, int kind, void* stream) {
+  if ((n & 1) || kind < 0 || kind > 2) return set_error("icd_act: odd element count or unknown activation");
+  launch_k(act_kernel, dim3(grid_for(n / 2)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+           reinterpret_cast<const __half2*>(x), reinterpret_cast<__half2*>(y), n / 2, kind);
+  return check_launch("act");
+}
+
+extern "C" int icd_embed_tokens(const long long* ids, const void* tok, const void* pos, void* out, long long rows, int T,
+                                int C, int vocab, void* stream) {
+  if (C % 8 != 0 || T < 1) return set_error("icd_embed_tokens: C must be a multiple of 8");
+  launch_k(embed_tokens_kernel, dim3(grid_for(rows * (C / 8))), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), ids,
+           reinterpret_cast<const uint4*>(tok), reinterpret_cast<const uint4*>(pos), reinterpret_cast<uint4*>(out), rows, T,
+           C / 8, vocab);
+  return check_launch("embed_tokens");
 }
 
 extern "C" int icd_add(const void* a, const void* b, void* y, long long n, void* stream) {

@@ -403,14 +403,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   }
 }
 
-// one warp per row, in place; three passes (row is L1/L2 resident)
-__global__ void __launch_bounds__(256) softmax_kernel(__half* __restrict__ x, long long rows, int cols, long long ld) {
+// one warp per row, in place; three passes (row is L1/L2 resident). causal_period > 0: row r is query r % period of
+// its sequence and attends to keys 0..(r % period) only (CLIP text transformer); the masked tail is written as 0.
+__global__ void __launch_bounds__(256) softmax_kernel(__half* __restrict__ x, long long rows, int cols, long long ld,
+                                                      int causal_period) {
   pdl_launch_dependents();
   pdl_wait();
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   __half* xr = x + warp * ld;
+  const int all_cols = cols;
+  if (causal_period > 0) cols = min(cols, static_cast<int>(warp % causal_period) + 1);
   float m = -INFINITY;
   for (int c = lane; c < cols; c += 32) m = fmaxf(m, __half2float(xr[c]));
 #pragma unroll
@@ -421,6 +425,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(__half* __restrict__ x, lo
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float inv = 1.f / s;
   for (int c = lane; c < cols; c += 32) xr[c] = __float2half_rn(__expf(__half2float(xr[c]) - m) * inv);
+  for (int c = cols + lane; c < all_cols; c += 32) xr[c] = __float2half_rn(0.f);
 }
 
 }  // namespace icd
@@ -529,9 +534,14 @@ extern "C" int icd_layernorm(const void* x, void* y, int rows, int C, float eps,
   return check_launch("layernorm");
 }
 
-extern "C" int icd_softmax(void* x, long long rows, int cols, long long ld, void* stream) {
+extern "C" int icd_softmax_causal(void* x, long long rows, int cols, long long ld, int causal_period, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long grid = (rows + 7) / 8;
-  launch_k(softmax_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, st, reinterpret_cast<__half*>(x), rows, cols, ld);
+  launch_k(softmax_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, st, reinterpret_cast<__half*>(x), rows, cols, ld,
+           causal_period);
   return check_launch("softmax");
+}
+
+extern "C" int icd_softmax(void* x, long long rows, int cols, long long ld, void* stream) {
+  return icd_softmax_causal(x, rows, cols, ld, 0, stream);
 }

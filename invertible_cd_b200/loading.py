@@ -143,16 +143,7 @@ def _unet_source(model_id, w_embed_dim, is_xl, device="cpu"):
     if cfg.time_cond_proj_dim and "time_embedding.cond_proj.weight" not in sd:
         # from_pretrained(time_cond_proj_dim=...) creates the layer with default init; the teacher .pt overwrites it
         sd["time_embedding.cond_proj.weight"] = torch.zeros(cfg.block_out_channels[0], cfg.time_cond_proj_dim)
-    text = {}
-    try:
-        from transformers import CLIPTextModel, CLIPTokenizer
-        if os.path.isdir(os.path.join(model_id, "tokenizer")):
-            text["tokenizer"] = CLIPTokenizer.from_pretrained(os.path.join(model_id, "tokenizer"))
-        if os.path.isdir(os.path.join(model_id, "text_encoder")):
-            text["text_encoder"] = CLIPTextModel.from_pretrained(os.path.join(model_id, "text_encoder"))
-    except Exception as e:  # text encoding is an input producer, not part of the accelerated path
-        print(f"[loading] text encoder/tokenizer not loaded: {e}")
-    return cfg, sd, text
+    return cfg, sd, _text_source(model_id, device)
 
 
 def _vae_source(model_id, device, is_xl):
@@ -174,6 +165,34 @@ def _vae_source(model_id, device, is_xl):
         if os.path.exists(p):
             return B200VAE(cfg, _load_tensor_file(p), device)
     return None
+
+
+def _text_source(model_id, device):
+    """Tokenizers (host side: transformers' CLIPTokenizer) and CLIP text encoders (B200CLIPTextModel on the sm_100a
+    kernels) of a local diffusers directory: `tokenizer[_2]/`, `text_encoder[_2]/{config.json, model.safetensors}`."""
+    from .text_encoder import B200CLIPTextModel, clip_text_config
+    text = {}
+    for suffix in ("", "_2"):
+        tdir, edir = os.path.join(model_id, "tokenizer" + suffix), os.path.join(model_id, "text_encoder" + suffix)
+        if os.path.isdir(tdir):
+            try:
+                from transformers import CLIPTokenizer
+                text["tokenizer" + suffix] = CLIPTokenizer.from_pretrained(tdir)
+            except Exception as e:
+                print(f"[loading] tokenizer{suffix} not loaded: {e}")
+        if os.path.isdir(edir):
+            with open(os.path.join(edir, "config.json")) as f:
+                raw = json.load(f)
+            base = vars(clip_text_config())
+            ccfg = clip_text_config(**{k: raw[k] for k in base if k in raw})
+            if "WithProjection" not in str(raw.get("architectures", "")):
+                ccfg.projection_dim = None
+            for fname in ("model.fp16.safetensors", "model.safetensors", "pytorch_model.bin"):
+                p = os.path.join(edir, fname)
+                if os.path.exists(p):
+                    text["text_encoder" + suffix] = B200CLIPTextModel(ccfg, _load_tensor_file(p), device)
+                    break
+    return text
 
 
 def _validate(cfg, sd):
@@ -216,8 +235,6 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
             print('PROVIDE TEACHER')
     _validate(cfg, sd)
     text_encoder = text.get("text_encoder")
-    if text_encoder is not None:
-        text_encoder = text_encoder.to(device)
     ldm_stable = ICDPipeline(B200UNet(cfg, sd, device), scheduler, _vae_source(model_id, device, False),
                              text.get("tokenizer"), text_encoder, device, tdtype)
     students = []
@@ -241,7 +258,8 @@ def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_che
     scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
     scheduler.num_train_timesteps = 1000
     stable_pipe = ICDPipeline(B200UNet(cfg, sd, device), scheduler, _vae_source(model_id, device, True),
-                              text.get("tokenizer"), text.get("text_encoder"), device, torch.float16)
+                              text.get("tokenizer"), text.get("text_encoder"), device, torch.float16,
+                              text.get("tokenizer_2"), text.get("text_encoder_2"))
     pipes = []
     for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
         print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')

@@ -250,11 +250,12 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     return out
 
 
-def softmax_(x, cols):
-    """In-place softmax over the first `cols` entries of the last dim of a [.., rows, ld] fp16 tensor."""
+def softmax_(x, cols, causal_period=0):
+    """In-place softmax over the first `cols` entries of the last dim of a [.., rows, ld] fp16 tensor.
+    `causal_period` T > 0: row r only sees keys 0..(r % T) (the rest of the row becomes 0)."""
     ld = x.stride(-2)
     rows = x.numel() // x.shape[-1]
-    _lib.check(_lib.load().icd_softmax(_ptr(x), rows, cols, ld, _stream()), "icd_softmax")
+    _lib.check(_lib.load().icd_softmax_causal(_ptr(x), rows, cols, ld, causal_period, _stream()), "icd_softmax")
     _count()
     return x
 
@@ -314,6 +315,29 @@ def silu(x, out=None):
     if out is None:
         out = torch.empty_like(x)
     _lib.check(_lib.load().icd_silu(_ptr(x), _ptr(out), x.numel(), _stream()), "icd_silu")
+    _count()
+    return out
+
+
+ACT_SILU, ACT_QUICK_GELU, ACT_GELU = 0, 1, 2
+
+
+def act(x, kind, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.load().icd_act(_ptr(x), _ptr(out), x.numel(), kind, _stream()), "icd_act")
+    _count()
+    return out
+
+
+def embed_tokens(ids, tok, pos, out=None):
+    """ids: int64 [B, T] (device) -> fp16 [B*T, C] = tok[ids] + pos[t]."""
+    B, T = ids.shape
+    Cc = tok.shape[1]
+    if out is None:
+        out = torch.empty((B * T, Cc), device=tok.device, dtype=torch.float16)
+    _lib.check(_lib.load().icd_embed_tokens(_ptr(ids), _ptr(tok), _ptr(pos), _ptr(out), B * T, T, Cc, tok.shape[0],
+                                            _stream()), "icd_embed_tokens")
     _count()
     return out
 
