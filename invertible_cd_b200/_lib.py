@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicd_b200.so")
+LIB_PATH = os.environ.get("ICD_LIB_PATH") or os.path.join(_HERE, "libicd_b200.so")   # ICD_LIB_PATH: debug builds
 
 # every symbol include/icd_b200.h declares (tests assert the library exports all of them)
 EXPORTED_SYMBOLS = [

@@ -239,6 +239,12 @@ static int launch_splitk_reduce(const float* ws, int splits, int M, int N, float
 
 using namespace icd;
 
+#ifdef ICD_GEMM_PROFILE
+// debug builds only (make GPROF=1): the clock64 stamps of the LAST gemm launch, [256 CTAs][32 slots] (managed memory)
+static long long* g_gemm_prof_buf = nullptr;
+extern "C" long long* icd_gemm_prof_buffer(void) { return g_gemm_prof_buf; }
+#endif
+
 extern "C" int icd_gemm_pick_bn(int M, int N, int Z, int geglu, int b_mn_major, int force_bn) {
   return pick_tile(M, N, Z, 16, geglu, b_mn_major, force_bn, 0, 1).bn;
 }
@@ -388,6 +394,14 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   if (p.upd_x != nullptr && !(p.out_fp32 && p.out_mode == GEMM_OUT_TRANSPOSED))
     return set_error("icd_gemm: fused update needs fp32 transposed output");
   p.exp_stats = reinterpret_cast<const float2*>(g->exp_stats);
+#ifdef ICD_GEMM_PROFILE
+  {
+    if (g_gemm_prof_buf == nullptr) cudaMallocManaged(&g_gemm_prof_buf, 256 * 32 * sizeof(long long));
+    p.prof = g_gemm_prof_buf;
+    const char* e = getenv("ICD_EPI_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+#endif
 
   p.kb_per_split = p.num_kb;   // single split: the whole K range (num_kb is final here)
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -448,7 +462,8 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
                        g->force_bm == 0 && g->force_splits == 0 && (g->force_bn == 0 || g->force_bn == 256) &&
                        g->a_z1_stride == 0 && g->a_z2_stride == 0 && g->b_z1_stride == 0 && g->b_z2_stride == 0 &&
                        gemm2sm_wanted(g->M, g->N, g->K0, g->geglu != 0);
-  const bool warp_epi = warp_epi_enabled && p.epi_tma && !g->geglu && !use_2sm;
+  const bool warp_epi = warp_epi_enabled && p.epi_tma && !g->geglu && !use_2sm &&
+                        (g->residual == nullptr || g->alpha == 1.0f);   // the MMA-added residual is not scaled by alpha
   if (p.epi_tma) {
     const uint64_t n_out = (uint64_t)(g->geglu ? g->N / 2 : g->N);
     const uint64_t z2 = (uint64_t)((g->Z + p.ZA1 - 1) / p.ZA1);
@@ -462,7 +477,14 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     if (g->residual != nullptr) {
       const uint64_t rdims[4] = {n_out, (uint64_t)g->M, 1, 1};
       const uint64_t rstr[3] = {(uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2, (uint64_t)g->ldr * 2};
-      if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, box, 64, 2)) return 1;
+      if (warp_epi) {
+        // EPI_WARP adds the residual on the tensor core: A-operand style atoms (64 columns x 128 rows, 128B swizzle)
+        const uint32_t rbox[4] = {64, 128, 1, 1};
+        if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, rbox, 128, 2)) return 1;
+        p.res_mma = 1;
+      } else if (make_tmap_4d(&tmRes, g->residual, rdims, rstr, box, 64, 2)) {
+        return 1;
+      }
     }
   }
 
@@ -496,10 +518,6 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
     return set_error("icd_gemm: GEGLU supports BN 128 / 256");
   }
   if (warp_epi) {
-    if (p.res_tma) {
-      if (bm == 256) { ICD_LAUNCH_BN(256, EPI_WARP_RES) }
-      ICD_LAUNCH_BN(128, EPI_WARP_RES)
-    }
     if (bm == 256) { ICD_LAUNCH_BN(256, EPI_WARP) }
     ICD_LAUNCH_BN(128, EPI_WARP)
   }

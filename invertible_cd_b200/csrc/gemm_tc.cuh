@@ -56,6 +56,10 @@ struct GemmParams {
   int epi_tma;            // 1: fp16 row-major output staged in smem (64B swizzle) and written with TMA stores;
                           //    the residual tile is prefetched into the same staging buffer by TMA
   int res_tma;            // residual present (epi_tma mode)
+  int res_mma;            // EPI_WARP: the residual is added on the TENSOR CORE — behind the K loop of every tile the
+                          // producer streams the [BM x 64] residual atoms of the tile through the A ring (tmRes: 128B
+                          // swizzle, box 64 x 128) and the issuer runs M128 x N16 x K16 MMAs of each 16-column chunk
+                          // against a 16x16 identity B tile: D[:, c..c+15] += R[:, c..c+15] . I  (exact in fp32)
   // fused consistency update (predicted_origin, utils/generation.py:136-155) on the conv_out tile:
   //   x_s = alpha_s * (x_t - sigma_t*eps) / alpha_t + sigma_s * eps      (same layout as the transposed output)
   const float* upd_x;     // current latent x_t (fp32, NCHW) or null
@@ -63,10 +67,28 @@ struct GemmParams {
   float alpha_t, sigma_t, alpha_s, sigma_s;
   // softmax-from-statistics (staged fp16 epilogue): out = exp2(alpha*acc - s.x) * s.y, s = exp_stats[z*M + row]
   const float2* exp_stats;
+#ifdef ICD_GEMM_PROFILE
+  long long* prof;        // [gridDim.x][32] clock64 stamps (debug builds: make GPROF=1, tools/gemm_prof.py)
+  int dbg;                // ICD_EPI_DEBUG bit mask: 1 skip the TMA store, 2 skip tcgen05.ld, 4 skip the bias/rowvec loads,
+                          // 8 skip fence.proxy.async, 16 skip st.shared, 32 skip bulk_wait + __syncwarp
+#endif
 };
 
+#ifdef ICD_GEMM_PROFILE
+#define ICD_DBG(bit) ((p.dbg & (bit)) != 0)
+#define ICD_GSTAMP(slot)                                                                       \
+  do {                                                                                         \
+    if (p.prof != nullptr && (slot) < 32) p.prof[blockIdx.x * 32 + (slot)] = clock64();        \
+  } while (0)
+#else
+#define ICD_DBG(bit) false
+#define ICD_GSTAMP(slot) \
+  do {                   \
+  } while (0)
+#endif
+
 enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3, EPI_STAGED_F32 = 4,
-             EPI_WARP = 5, EPI_WARP_RES = 6 };
+             EPI_WARP = 5 };
 
 template <int BM_, int BN, int EPI>
 struct GemmCfg {
@@ -76,8 +98,9 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int C_BYTES = 4 * 8192;  // epilogue staging: 4 atoms of [128 rows x 32 cols] fp16, 64B swizzle
-  // TMA-loaded residual: 2 x 16 KB units (EPI_STAGED_RES) or 8 warps x 2 x 2 KB (EPI_WARP_RES)
-  static constexpr int R_BYTES = (EPI == EPI_STAGED_RES || EPI == EPI_WARP_RES) ? 4 * 8192 : 0;
+  // EPI_STAGED_RES: TMA-loaded residual units (2 x 16 KB). EPI_WARP: the 16x16 identity B tile (128B-swizzled,
+  // 1024-byte aligned) of the tensor-core residual add
+  static constexpr int R_BYTES = (EPI == EPI_STAGED_RES) ? 4 * 8192 : (EPI == EPI_WARP ? 2048 : 0);
   static constexpr int BAR_BYTES = 512;
   static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - C_BYTES - R_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
@@ -112,13 +135,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* res_full = bars + 2 * STAGES + 4;    // [2] residual unit landed in smem_r (TMA tx-count)
   uint64_t* res_empty = bars + 2 * STAGES + 6;   // [2] residual unit consumed by the 128 epilogue threads
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
-  uint64_t* wres_bar = bars + 2 * STAGES + 9;    // [8 warps][2] per-warp residual sub-tile landed (EPI_WARP_RES)
-  static_assert((2 * 8 + 9 + 16) * 8 <= Cfg::BAR_BYTES, "barrier block");
+  static_assert((2 * 8 + 9) * 8 <= Cfg::BAR_BYTES, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   pdl_launch_dependents();   // the next kernel may become resident as CTAs of this one retire (its prologue overlaps our tail)
+  if (threadIdx.x == 0) ICD_GSTAMP(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -135,18 +158,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(&res_full[i], 1);
       mbar_init(&res_empty[i], Cfg::EPI_THREADS);
     }
-    for (int i = 0; i < 16; ++i) mbar_init(&wres_bar[i], 1);
+
     tma_prefetch_desc(&tmOut);
     tma_prefetch_desc(&tmRes);
     fence_mbar_init();
   } else if (warp == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  } else if (warp == 2) {
+    if constexpr (EPI == EPI_WARP) {
+      // 16x16 fp16 identity as a K-major, 128B-swizzled B tile (16 rows x 128 B; only the first K16 chunk is read)
+      uint32_t* idt = reinterpret_cast<uint32_t*>(smem_r);
+      for (int i = lane; i < 512; i += 32) idt[i] = 0u;
+      __syncwarp();
+      if (lane < 16) {
+        const int n = lane;
+        const uint32_t off = n * 128 + ((((n * 2) >> 4) ^ (n & 7)) << 4) + ((n * 2) & 15);
+        *reinterpret_cast<__half*>(smem_r + off) = __float2half_rn(1.0f);
+      }
+      fence_proxy_async_smem();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) ICD_GSTAMP(1);
   pdl_wait();                // everything above ran under the previous kernel's tail; global memory is touched below
+  if (threadIdx.x == 0) ICD_GSTAMP(2);
 
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -220,7 +258,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if constexpr (EPI == EPI_WARP) {
+          if (p.res_mma) {   // residual atoms [BM x 64] of this tile, streamed through the A half of the ring
+            const int ncols = min(BN, p.N - n0);
+            for (int atom = 0; atom * 64 < ncols; ++atom) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], HALVES * 16384);
+#pragma unroll
+              for (int h = 0; h < HALVES; ++h)
+                tma_load_4d(smem_a + stage * Cfg::A_BYTES + h * 16384, &tmRes, &full_bar[stage], n0 + atom * 64, m0h[h], 0,
+                            0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
       }
+      ICD_GSTAMP(3);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -249,6 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (iter == 0 && kb == kb_begin) ICD_GSTAMP(4);
           const uint32_t a_lo = a_lo0 + stage * (Cfg::A_BYTES >> 4);
           const uint32_t b_lo = b_lo0 + stage * (Cfg::B_BYTES >> 4);
           const uint32_t first = (kb > kb_begin) ? 1u : 0u;
@@ -262,10 +316,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == kb_end - 1) umma_commit(&tmem_full[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if constexpr (EPI == EPI_WARP) {
+          if (p.res_mma) {   // D[:, c .. c+15] += R[:, c .. c+15] . I16 for every 16-column chunk of the tile
+            const int tz = tile - split * tiles_all_z;
+            const int tt = tz - (tz / tiles_per_z) * tiles_per_z;
+            const int ncols = min(BN, p.N - (tt % n_tiles) * BN);
+            const uint32_t idesc16 = umma_idesc_f16(128, 16, false, false);
+            const uint64_t db_id = (static_cast<uint64_t>(desc_hi) << 32) | (((smem_u32(smem_r) >> 4) & 0x3FFFu) | (1u << 16));
+            for (int atom = 0; atom * 64 < ncols; ++atom) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t a_lo = a_lo0 + stage * (Cfg::A_BYTES >> 4);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (atom * 64 + c * 16 < ncols) {
+#pragma unroll
+                  for (int h = 0; h < HALVES; ++h)
+                    umma_f16_ss(d_tmem + h * Cfg::HALF_STRIDE + atom * 64 + c * 16,
+                                (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + h * (16384u >> 4) + c * 2u), db_id,
+                                idesc16, 1u);
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        ICD_GSTAMP(8 + 3 * iter);          // all MMAs of tile `iter` issued
       }
+      ICD_GSTAMP(5);
     }
   } else if (warp == 10) {
     // ------------------------------------------------------------------ residual producer (EPI_STAGED_RES only)
@@ -363,25 +445,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       if (leader) bulk_wait0();
-    } else if constexpr (EPI == EPI_WARP || EPI == EPI_WARP_RES) {
+    } else if constexpr (EPI == EPI_WARP) {
       // ---- per-warp staged epilogue: every epilogue warp owns a [32 rows x 32 columns] block of each 64-column unit
       // (rows = its TMEM lane quadrant, columns = its half of the unit) and runs its own pipeline
-      //   tcgen05.ld -> (+bias / rowvec / residual | softmax-from-stats) -> 64B-swizzled smem block -> TMA store,
+      //   tcgen05.ld -> (alpha, +bias, +rowvec | softmax-from-stats) -> 64B-swizzled smem block -> TMA store,
       // double-buffered per warp, with NO CTA-wide barrier: the only shared event is the release of the accumulator.
-      // The residual block is fetched by the warp's own TMA load one step ahead (the first one of a tile before the
-      // accumulator is awaited, i.e. behind the tile's main loop).
-      constexpr bool RES = (EPI == EPI_WARP_RES);
+      // The RESIDUAL never reaches this code: it is added on the tensor core (identity MMA behind the K loop, see the
+      // producer / issuer), so the accumulator already holds acc + residual in fp32.
+      // The loop body is kept lean on purpose: the K = N = C transformer linears are bound by the INSTRUCTION ISSUE of
+      // this epilogue (measured, profiles/r2_gemm_k320_*: ~500 instructions per 32x32 block before this rewrite).
       constexpr int outw = BN;
       constexpr int units = (outw + 63) / 64;
-      constexpr int steps = HALVES * units;          // (half, unit) pairs of one tile, in processing order
       const int ew = warp - 2;                       // 0..7
       uint8_t* my_out = smem_c + ew * 4096;          // 2 x [32 rows x 64 B]
-      uint8_t* my_res = smem_r + ew * 4096;
-      uint64_t* my_bar = wres_bar + ew * 2;
       const bool lane0 = lane == 0;
       const uint32_t sw = (lane >> 1) & 3;           // 64B swizzle: 16B-chunk index ^= (row / 2) % 4
       const int col_w = part * 32;                   // this warp's column offset inside a 64-column unit
-      uint32_t ocount = 0, rcount = 0;               // staged blocks written / residual blocks consumed by this warp
+      const bool has_bias = p.bias != nullptr, has_rv = p.rowvec != nullptr, has_est = p.exp_stats != nullptr;
+      const bool unit_alpha = p.alpha == 1.0f;
+      uint32_t ocount = 0;                           // staged blocks written by this warp
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         const int tz = tile % tiles_all_z;
         const int z = tz / tiles_per_z;
@@ -390,104 +472,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int acc = iter % ACC_STAGES;
         const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
         const int n_out0 = nt * outw;
-        auto step_active = [&](int s) {            // warp-uniform: does this warp have columns in step s?
-          const int u = s % units;
-          const int c = u * 64 + col_w;
-          return s < steps && c < outw && n_out0 + c < p.N;
-        };
-        auto issue_res = [&](int s, uint32_t rc) {   // lane 0: TMA-load the residual block of step s into buffer rc & 1
-          const int half = s / units, u = s % units;
-          mbar_expect_tx(&my_bar[rc & 1], 2048);
-          tma_load_4d(my_res + (rc & 1) * 2048, &tmRes, &my_bar[rc & 1], n_out0 + u * 64 + col_w,
-                      mt * BM + half * 128 + quad * 32, 0, 0);
-        };
-        int s = 0;
-        while (s < steps && !step_active(s)) ++s;      // first step in which this warp has columns
-        if (RES && lane0 && s < steps) issue_res(s, rcount);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        if (warp == 2 && lane0) ICD_GSTAMP(9 + 3 * iter);
 #pragma unroll 1
-        while (s < steps) {
-          int nx = s + 1;
-          while (nx < steps && !step_active(nx)) ++nx; // next one (BN = 160: the upper column half skips every third unit)
-          const int half = s / units, u = s % units;
-          const int col_t = u * 64 + col_w;
-          const int ncol = n_out0 + col_t;
+        for (int half = 0; half < HALVES; ++half) {
           const int row0 = mt * BM + half * 128 + quad * 32;
           const int row = row0 + lane;
-          if (RES && lane0 && nx < steps) issue_res(nx, rcount + 1);
-          // this warp's staging buffer (ocount & 1) was last used two blocks ago: its TMA store must have read it
-          if (lane0) bulk_wait_read1();
-          __syncwarp();
-          float v[32];
-          tmem_ld32(tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE + (static_cast<uint32_t>(quad * 32) << 16) +
-                        col_t,
-                    v);
-          tmem_ld_wait();
-          const int img = min(row, p.M - 1) / p.rows_per_img;
-          const float* rv = (p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(img) * p.ldv : nullptr;
+          const float* rv = nullptr;
+          if (has_rv) rv = p.rowvec + static_cast<long long>(min(row, p.M - 1) / p.rows_per_img) * p.ldv;
+          float2 est = make_float2(0.f, 0.f);
+          if (has_est && row < p.M) est = __ldg(p.exp_stats + static_cast<long long>(z) * p.M + row);
+          const uint32_t t_half =
+              tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+          for (int u = 0; u < units; ++u) {
+            const int col_t = u * 64 + col_w;
+            const int ncol = n_out0 + col_t;
+            if (col_t >= outw || ncol >= p.N) continue;   // warp-uniform (BN = 160: the upper half skips unit 2)
+            // this warp's staging buffer (ocount & 1) was last used two blocks ago: its TMA store must have read it
+            if (lane0) bulk_wait_read1();
+            __syncwarp();
+            float v[32];
+            tmem_ld32(t_half + col_t, v);
+            tmem_ld_wait();
+            if (!unit_alpha) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (ncol + j4 * 4 < p.N) {   // N % 8 == 0 in staged mode: whole groups
-              if (p.bias != nullptr) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + j4);
-              if (rv != nullptr) b1 = __ldg(reinterpret_cast<const float4*>(rv + ncol) + j4);
+              for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
             }
-            v[j4 * 4 + 0] = v[j4 * 4 + 0] * p.alpha + (b0.x + b1.x);
-            v[j4 * 4 + 1] = v[j4 * 4 + 1] * p.alpha + (b0.y + b1.y);
-            v[j4 * 4 + 2] = v[j4 * 4 + 2] * p.alpha + (b0.z + b1.z);
-            v[j4 * 4 + 3] = v[j4 * 4 + 3] * p.alpha + (b0.w + b1.w);
-          }
-          if (p.exp_stats != nullptr) {   // warp-uniform
-            float2 est = make_float2(0.f, 0.f);
-            if (row < p.M) est = __ldg(p.exp_stats + static_cast<long long>(z) * p.M + row);
+            if (ncol + 32 <= p.N) {   // whole block inside the matrix (always, except ragged N tails)
+              if (has_bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = exp2f(v[j] - est.x) * est.y;
-          }
-          if constexpr (RES) mbar_wait(&my_bar[rcount & 1], (rcount >> 1) & 1);
-          const uint32_t obuf = smem_u32(my_out) + (ocount & 1) * 2048 + lane * 64;
-          const uint32_t rbuf = smem_u32(my_res) + (rcount & 1) * 2048 + lane * 64;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t o[4];
-            if constexpr (RES) {
-              uint4 rr;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w)
-                           : "r"(rbuf + ((cc ^ sw) << 4)));
-              const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[q]));
-                const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q] + f.x, v[cc * 8 + 2 * q + 1] + f.y);
-                o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + j4);
+                  v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+                }
               }
-            } else {
+              if (has_rv) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(rv + ncol) + j4);
+                  v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+                }
+              }
+            } else {                  // N % 8 == 0 in staged mode: whole groups of 4
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                if (ncol + j4 * 4 < p.N) {
+                  if (has_bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + j4);
+                    v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+                  }
+                  if (has_rv) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(rv + ncol) + j4);
+                    v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+                  }
+                }
+              }
+            }
+            if (has_est) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = exp2f(v[j] - est.x) * est.y;
+            }
+            const uint32_t obuf = smem_u32(my_out) + (ocount & 1) * 2048 + lane * 64;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t o[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const __half2 h2 = __floats2half2_rn(v[cc * 8 + 2 * q], v[cc * 8 + 2 * q + 1]);
                 o[q] = *reinterpret_cast<const uint32_t*>(&h2);
               }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obuf + ((cc ^ sw) << 4)), "r"(o[0]),
+                           "r"(o[1]), "r"(o[2]), "r"(o[3])
+                           : "memory");
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obuf + ((cc ^ sw) << 4)), "r"(o[0]), "r"(o[1]),
-                         "r"(o[2]), "r"(o[3])
-                         : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane0) {
+              tma_store_4d(&tmOut, my_out + (ocount & 1) * 2048, ncol, row0, z % p.ZA1, z / p.ZA1);
+              bulk_commit();
+            }
+            ++ocount;
           }
-          if constexpr (RES) ++rcount;
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane0) {
-            tma_store_4d(&tmOut, my_out + (ocount & 1) * 2048, ncol, row0, z % p.ZA1, z / p.ZA1);
-            bulk_commit();
-          }
-          ++ocount;
-          s = nx;
         }
         // every TMEM read of this accumulator by this thread is complete (tmem_ld_wait above)
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
+        if (warp == 2 && lane0) ICD_GSTAMP(10 + 3 * iter);
       }
       if (lane0) bulk_wait0();
+      if (warp == 2 && lane0) ICD_GSTAMP(6);
     } else if constexpr (EPI != EPI_DIRECT) {
       // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual | GEGLU) -> swizzled smem -> TMA store.
       // Output is produced in 64-column units through a double-buffered staging area (2 x [128 rows x 64 cols],
@@ -748,6 +823,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) ICD_GSTAMP(7);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
