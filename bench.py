@@ -273,8 +273,11 @@ def _build_ours(wl, device):
         del stable, fwd
         rev.vae = None        # the metric is latents/s (VAE excluded): sample_deterministic must not decode
         return None, rev, None
-    ldm, rev, fwd = loading.load_models(wl["model"], device, "synthetic:1", None, r=64, w_embed_dim=512,
+    ldm, rev, fwd = loading.load_models(wl["model"], device, "synthetic:1", "synthetic:2", r=64, w_embed_dim=512,
                                         dtype="fp16")
+    for pipe in (ldm, rev, fwd):
+        if pipe is not None:
+            pipe.vae = None   # the metric is latents/s (VAE excluded): cons_inversion must not decode
     solver = generation.Generator(model=ldm, n_steps=50, noise_scheduler=DDPMScheduler(), forward_cons_model=fwd,
                                   reverse_cons_model=rev, reverse_timesteps=list(wl["reverse"]),
                                   forward_timesteps=list(wl["forward"]))
@@ -547,6 +550,102 @@ def measure(wl_key, B, args, rank, world, local_rank, device, full, capture_self
     return rec
 
 
+class _WordTokenizer:
+    """Whitespace tokenizer with the three members the p2p helpers use (the edit controllers align prompts by token;
+    there are no CLIP vocabulary files offline)."""
+    model_max_length = 77
+
+    def __init__(self):
+        self.vocab, self.inv = {}, {1: "<s>", 2: "</s>"}
+
+    def encode(self, text):
+        ids = [1]
+        for w in text.split():
+            if w not in self.vocab:
+                self.vocab[w] = len(self.vocab) + 3
+                self.inv[self.vocab[w]] = w
+            ids.append(self.vocab[w])
+        return ids + [2]
+
+    def decode(self, ids):
+        return "".join(self.inv[i] for i in ids)
+
+
+def measure_small_batch(device, iters=10):
+    """BASELINE configs[0] / configs[2] shapes, end to end through the public API on one GPU:
+      b1_generation  4-step reverse generation of ONE prompt (1 U-Net row; the loop replays from the library's graph cache)
+      cfg2_edit      forward-consistency inversion of one latent (4 steps, w = 0) followed by the 4-step reverse edit
+                     of [source, edited] prompts with an AttentionRefine + LocalBlend controller (2 conditional rows ==
+                     the reference's 4-row U-Net batch); edit controllers run eagerly (stateful Python, graphs.py)."""
+    from invertible_cd_b200 import generation, inversion, p2p
+    wl = WORKLOADS["sd15"]
+    ldm, rev, solver = build_ours(wl, device)
+    g = torch.Generator().manual_seed(7)
+    ctx = torch.randn(2, 77, wl["ctx_dim"], generator=g).half().pin_memory()
+    img_lat = (torch.randn(1, 4, 64, 64, generator=g) * 0.5).pin_memory()
+    x_T = torch.randn(1, 4, 64, 64, generator=g).pin_memory()
+    prompts = ["a photo of a house on a mountain", "a photo of a house on a mountain at winter evening"]
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(iters):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / iters
+
+    def gen_b1():
+        store = p2p.AttentionStore()
+        store.capture_self = False
+        lat, _ = generation.runner(model=rev, prompt=ctx[1:], controller=store, solver=solver, is_cons_forward=True,
+                                   guidance_scale=wl["guidance"], latent=x_T, return_type="latent", tau1=1.0, tau2=1.0,
+                                   w_embed_dim=512)
+        return lat.to("cpu")
+
+    ms = timed(gen_b1)
+    out["b1_generation"] = {"ms_per_latent": ms, "value": 1e3 / ms, "unit": "latents/s",
+                            "what": "4-step reverse generation of 1 prompt through generation.runner, host inputs"}
+
+    def edit():
+        (_, _), x_inv, _ = inversion.invert(solver, stop_step=50, is_cons_inversion=True, inv_guidance_scale=0.0,
+                                            w_embed_dim=512, image_path=img_lat.to(device, non_blocking=True),
+                                            prompt=ctx[:1], seed=3)
+        p2p.tokenizer, p2p.device, p2p.NUM_DDIM_STEPS = _WordTokenizer(), device, 4
+        ctrl = p2p.make_controller(prompts, False, {"default_": 0.3}, 0.6, (("mountain",), ("mountain",)), None)
+        lat, _ = generation.runner(model=rev, prompt=ctx, controller=ctrl, solver=solver, is_cons_forward=True,
+                                   guidance_scale=wl["guidance"], latent=x_inv, return_type="latent", tau1=0.8, tau2=0.8,
+                                   w_embed_dim=512)
+        return lat.to("cpu")
+
+    try:
+        ms = timed(edit)
+        out["cfg2_edit"] = {"ms_per_edit": ms, "value": 1e3 / ms, "unit": "edits/s",
+                            "what": "BASELINE configs[2] for one image: 4-step forward inversion (w=0, graph cache) + 4-step "
+                                    "reverse edit of [source, edit] with AttentionRefine + LocalBlend (eager), latents in / "
+                                    "latents out, host inputs"}
+    except Exception as e:
+        out["cfg2_edit"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    p2p.register_attention_control(rev, None)
+    # the step after the loop (SURVEY §8f-1): VAE decode of 8 latents to 512^2 images on the same kernels
+    try:
+        from invertible_cd_b200 import loading
+        vae = loading._vae_source("synthetic", device, False)
+        z = torch.randn(8, 4, 64, 64, generator=g).to(device)
+        ms = timed(lambda: vae.decode(z)["sample"])
+        out["vae_decode_b8"] = {"ms_per_batch": ms, "value": 8e3 / ms, "unit": "images/s",
+                                "what": "AutoencoderKL decode of 8 latents -> 8 x 3 x 512 x 512 (eager launches), "
+                                        "device-resident in and out; not part of the latents/s metric"}
+        del vae
+    except Exception as e:
+        out["vae_decode_b8"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -644,6 +743,11 @@ def main():
 
     top = measure(top_key, wl["per_gpu_batch"], args, rank, world, local_rank, device, full=True)
     extra = {}
+    if args.workload == "all" and world == 1:
+        try:
+            extra["small_batch"] = measure_small_batch(device)
+        except Exception as e:
+            extra["small_batch"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
     if args.workload == "all":
         torch.cuda.empty_cache()
         if world == 1:

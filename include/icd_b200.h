@@ -116,9 +116,9 @@ int icd_attention_ex(const void* q, const void* k, const void* v, void* out, int
  * (diffusers ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out).
  * One launch (single pass: the activation chunk of every CTA stays in shared memory between the statistics and the
  * normalisation) when the whole tensor fits on chip, otherwise two (statistics, apply).
- * The single-pass kernel synchronises the CTAs of an image through a per-device counter array: like the reference
- * (one stream, one in-flight call per pipeline), do not run two icd_groupnorm calls concurrently on different
- * streams of the same device (set ICD_GN_FUSED=0 to force the two-kernel path if you must). */
+ * The single-pass kernel is launched COOPERATIVELY (the driver co-schedules all of its CTAs or refuses the launch, in
+ * which case the two-kernel path runs) and synchronises through cooperative-groups' grid barrier: no library-global
+ * state, safe on concurrent streams and across CUDA-graph replays. 32 groups; channels per group 4 or >= 8. */
 int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, void* y, int B, int HW, int groups, float eps,
                   const float* gamma, const float* beta, int apply_silu, float* stats_ws, void* stream);
 /* Number of kernel launches icd_groupnorm will use for this shape (1 = single pass, 2 = statistics + apply). */

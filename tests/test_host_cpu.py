@@ -456,7 +456,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.icd_abi_version() == 1
+    assert lib.icd_abi_version() == 2
     import ctypes
     assert ctypes.sizeof(_lib.IcdGemm) == 312
 

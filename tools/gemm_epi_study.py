@@ -10,8 +10,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from invertible_cd_b200 import ops  # noqa: E402
 from tools._timing import time_us  # noqa: E402
 
-SHAPES = [(32768, 320, 320), (8192, 640, 640), (2048, 1280, 1280), (4096, 1280, 1280), (16384, 640, 640)]
-TILES = [(0, 0), (128, 160), (256, 160), (128, 128), (128, 64), (128, 256)]
+SHAPES = [(32768, 320, 320), (8192, 640, 640), (2048, 1280, 1280), (4096, 1280, 1280), (16384, 640, 640),
+          (32768, 320, 1280), (8192, 640, 2560), (2048, 1280, 5120), (4096, 1280, 5120), (16384, 640, 2560),
+          (32768, 960, 320), (8192, 1920, 640), (16384, 1920, 640), (512, 1280, 1280), (65536, 320, 320)]
+TILES = [(0, 0), (128, 160), (256, 160), (128, 128), (256, 128), (128, 256), (256, 64), (256, 256)]
 
 
 def main():
