@@ -36,9 +36,9 @@ GATES = {
     "cfg1_loop": (5e-4, 6.5e-4),               # measured 2.48e-4, 3.07e-4
     "cfg1_store_cross": (None, 1.3e-4),        # measured max |err| 6.0e-5 (probabilities averaged over the 4 steps)
     "cfg1_store_self": (None, 1e-4),           # measured max |err| 4.7e-5
-    "cfg3_loop": (4e-3, 2e-2),
-    "teacher_ddim_edit": (4e-3, 2e-2),
-    "cons_edit_localblend": (4e-3, 2e-2),
+    "cfg3_loop": (1.1e-3, 2.2e-3),             # measured 5.09e-4, 1.09e-3
+    "teacher_ddim_edit": (3.5e-3, 3.4e-3),     # measured 1.73e-3, 1.67e-3 (6 DDIM steps, CFG 7.5, edit + LocalBlend)
+    "cons_edit_localblend": (5e-4, 5.5e-4),    # measured 2.48e-4, 2.63e-4
 }
 
 
