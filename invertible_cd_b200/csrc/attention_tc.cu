@@ -34,6 +34,10 @@ namespace icd {
 
 int make_tmap_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_b[3],
                  const uint32_t box[4], int swizzle_bytes, int elem_bytes);
+// attention_smallkv.cu: N_kv <= 80 (text context). -1 = not eligible, 0 = launched, 1 = error.
+int attention_smallkv_dispatch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
+                               int D, long long q_ld, long long k_ld, long long v_ld, long long out_ld, float scale,
+                               void* probs_out, long long probs_ld, float* stats_out, cudaStream_t st);
 
 struct AttnParams {
   int B, H, Nq, Nk;
@@ -547,6 +551,11 @@ extern "C" int icd_attention_ex(const void* q, const void* k, const void* v, voi
   if (probs_out != nullptr && Nk > 128)
     return set_error("icd_attention: probability capture is fused only for N_kv <= 128 (use the explicit path)");
   if ((D % 8) != 0) return set_error("icd_attention: head dim must be a multiple of 8");
+  if (Nk <= 80) {   // cross-attention over the text context: one CTA walks a run of query tiles (attention_smallkv.cu)
+    const int r = attention_smallkv_dispatch(q, k, v, out, B, H, Nq, Nk, D, q_ld, k_ld, v_ld, out_ld, scale, probs_out,
+                                             probs_ld, stats_out, reinterpret_cast<cudaStream_t>(stream));
+    if (r >= 0) return r;
+  }
   CUtensorMap tq, tk, tv;
   // tensor maps over [B][N][H][D] as dims (d, head, token, batch): strides grow monotonically
   const uint32_t box[4] = {64, 1, 128, 1};      // Q: 128 query rows

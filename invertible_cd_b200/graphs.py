@@ -95,6 +95,9 @@ def run(owner, key, inputs, body):
     """`owner`: the B200UNet the loop runs (holds the cache). `body(*static_inputs) -> (outputs, aux)`: outputs is a list of CUDA tensors, aux any Python object created
     inside (kept alive with the graph). Returns (static outputs — valid until the next call with this key, aux)."""
     _cache = _cache_of(owner)
+    activate = getattr(owner, "activate", None)     # unet.AdapterView: make its LoRA adapter the resident one
+    if activate is not None:
+        activate()
     entry = _cache.get(key)
     if entry is None:
         static_in = [x.clone() for x in inputs]

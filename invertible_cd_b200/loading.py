@@ -216,12 +216,38 @@ def _lora_source(spec, cfg, r, device="cpu"):
     return _load_tensor_file(spec)
 
 
+def _adapter_mode(adapters):
+    mode = adapters if adapters is not None else os.environ.get("ICD_LORA_ADAPTERS", "resident")
+    if mode not in ("resident", "swap"):
+        raise ValueError(f"adapters must be 'resident' or 'swap', got {mode!r}")
+    return mode
+
+
+def _students_swap(teacher_pipe, shared, cfg, ckpts, r, device, lora_dtype):
+    """One packed U-Net for the teacher and both students: the checkpoints become hot-swappable adapters of `shared`
+    (B200UNet.add_adapter); every pipeline's `.unet` is an AdapterView that activates its adapter on use."""
+    teacher_pipe.unet = shared.adapter_view(None)
+    out = []
+    for name, ckpt in ckpts:
+        if ckpt is None:
+            out.append(None)
+            continue
+        print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"} (hot-swappable adapter)')
+        shared.add_adapter(name.lower(), _lora_source(ckpt, cfg, r, device), lora_dtype=lora_dtype)
+        out.append(teacher_pipe.clone_with_unet(shared.adapter_view(name.lower())))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- public API
 def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, w_embed_dim=0,
-                teacher_checkpoint=None, dtype='fp32'):
+                teacher_checkpoint=None, dtype='fp32', adapters=None):
     """-> (ldm_stable, reverse_cons_model, forward_cons_model), as utils/loading.py:27-90.
     `dtype` selects the dtype of the latents the loop carries ('fp32'/'fp16'); the U-Net kernels always compute in
-    fp16 with fp32 accumulation (documented deviation: the reference's fp32 editing mode runs fp32 cuBLAS/cuDNN)."""
+    fp16 with fp32 accumulation (documented deviation: the reference's fp32 editing mode runs fp32 cuBLAS/cuDNN).
+    `adapters` (extension; default from ICD_LORA_ADAPTERS, else 'resident'): 'resident' keeps three packed U-Nets as
+    the reference keeps three pipelines; 'swap' keeps ONE plus the low-rank factors and re-fuses on the GPU when a
+    different model is called (unet.B200UNet.set_adapter)."""
+    mode = _adapter_mode(adapters)
     tdtype = torch.float32 if dtype == 'fp32' else torch.float16
     scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
                               set_alpha_to_one=False)
@@ -237,6 +263,11 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
     text_encoder = text.get("text_encoder")
     ldm_stable = ICDPipeline(B200UNet(cfg, sd, device), scheduler, _vae_source(model_id, device, False),
                              text.get("tokenizer"), text_encoder, device, tdtype)
+    if mode == "swap":
+        rev, fwd = _students_swap(ldm_stable, ldm_stable.unet, cfg,
+                                  (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)), r, device,
+                                  torch.float16)
+        return ldm_stable, rev, fwd
     students = []
     for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
         if ckpt is None:
@@ -248,8 +279,11 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
     return ldm_stable, students[0], students[1]
 
 
-def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_checkpoint, device="cuda", r=64):
-    """-> (stable_pipe, pipe, forw_pipe), as utils/loading.py:93-147 (fp16 base, LoRA kept fp32 for the fuse)."""
+def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_checkpoint, device="cuda", r=64,
+                   adapters=None):
+    """-> (stable_pipe, pipe, forw_pipe), as utils/loading.py:93-147 (fp16 base, LoRA kept fp32 for the fuse).
+    `adapters`: see load_models (in 'swap' mode the factors are rounded to the fp16 operands of the fuse GEMM)."""
+    mode = _adapter_mode(adapters)
     cfg, sd, text = _unet_source(model_id, 512, is_xl=True, device=device)
     if teacher_checkpoint is not None:
         sd = teacher_checkpoint if isinstance(teacher_checkpoint, dict) else _load_tensor_file(teacher_checkpoint)
@@ -260,6 +294,11 @@ def load_models_xl(model_id, reverse_checkpoint, forward_checkpoint, teacher_che
     stable_pipe = ICDPipeline(B200UNet(cfg, sd, device), scheduler, _vae_source(model_id, device, True),
                               text.get("tokenizer"), text.get("text_encoder"), device, torch.float16,
                               text.get("tokenizer_2"), text.get("text_encoder_2"))
+    if mode == "swap":
+        rev, fwd = _students_swap(stable_pipe, stable_pipe.unet, cfg,
+                                  (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)), r, device,
+                                  torch.float32)
+        return stable_pipe, rev, fwd
     pipes = []
     for name, ckpt in (("Reverse", reverse_checkpoint), ("Forward", forward_checkpoint)):
         print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')

@@ -18,10 +18,11 @@ def pack_linear(w):
     return w.reshape(w.shape[0], -1).to(torch.float16).contiguous()
 
 
-def pack_geglu(w, b, bn):
+def pack_geglu(w, b, bn, return_perm=False):
     """GEGLU projection (ff.net.0.proj: [2F, K], chunk -> hidden | gate): interleave per BN-wide output tile as
     [BN/2 hidden rows | BN/2 matching gate rows] so the GEMM epilogue sees h_j and g_j of the same row in one
-    TMEM accumulator tile. Returns (w_packed fp16 [2F, K], bias_packed fp32 [2F])."""
+    TMEM accumulator tile. Returns (w_packed fp16 [2F, K], bias_packed fp32 [2F]) and, with `return_perm`, the row
+    permutation (packed row i = original row perm[i]; a LoRA factor B is permuted the same way)."""
     two_f = w.shape[0]
     f = two_f // 2
     half = bn // 2
@@ -32,4 +33,5 @@ def pack_geglu(w, b, bn):
         idx.extend(range(t * half, (t + 1) * half))
         idx.extend(range(f + t * half, f + (t + 1) * half))
     idx = torch.tensor(idx, device=w.device)
-    return w[idx].to(torch.float16).contiguous(), b[idx].to(torch.float32).contiguous()
+    wp, bp = w[idx].to(torch.float16).contiguous(), b[idx].to(torch.float32).contiguous()
+    return (wp, bp, idx) if return_perm else (wp, bp)

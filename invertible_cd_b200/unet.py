@@ -88,13 +88,23 @@ class B200UNet:
         self._temb_off = 0
         kv_w = []
         self._kv_off = 0
+        # diffusers module path -> (kind, getter of the packed tensor, first row, rows, row permutation): where a LoRA
+        # delta B.A of that module lands in the packed weights (adapters below)
+        self._wmap = {}
+
+        def reg(mod, kind, getter, row0, nrows, perm=None):
+            self._wmap[mod] = (kind, getter, row0, nrows, perm)
 
         def conv(prefix):
-            return SimpleNamespace(w=pack_conv3x3(g(prefix + ".weight")).to(dev), b=_f32(g(prefix + ".bias"), dev))
+            ns = SimpleNamespace(w=pack_conv3x3(g(prefix + ".weight")).to(dev), b=_f32(g(prefix + ".bias"), dev))
+            reg(prefix, "conv", lambda: ns.w, 0, ns.w.shape[0])
+            return ns
 
         def lin(prefix, bias=True):
-            return SimpleNamespace(w=pack_linear(g(prefix + ".weight")).to(dev),
-                                   b=_f32(g(prefix + ".bias"), dev) if bias else None)
+            ns = SimpleNamespace(w=pack_linear(g(prefix + ".weight")).to(dev),
+                                 b=_f32(g(prefix + ".bias"), dev) if bias else None)
+            reg(prefix, "linear", lambda: ns.w, 0, ns.w.shape[0])
+            return ns
 
         def norm(prefix):
             return SimpleNamespace(g=_f32(g(prefix + ".weight"), dev), b=_f32(g(prefix + ".bias"), dev))
@@ -105,13 +115,14 @@ class B200UNet:
                                 shortcut=lin(prefix + ".conv_shortcut") if cin != cout else None)
             temb_w.append(g(prefix + ".time_emb_proj.weight"))
             temb_b.append(g(prefix + ".time_emb_proj.bias"))
+            reg(prefix + ".time_emb_proj", "linear", lambda: self.temb_all.w, self._temb_off, cout)
             self._temb_off += cout
             return r
 
         def attn_block(prefix, C, heads, place):
             a1, a2 = prefix + ".attn1", prefix + ".attn2"
-            w1, b1 = pack_geglu(g(prefix + ".ff.net.0.proj.weight").to(dev), g(prefix + ".ff.net.0.proj.bias").to(dev),
-                                GEGLU_BN)
+            w1, b1, perm = pack_geglu(g(prefix + ".ff.net.0.proj.weight").to(dev),
+                                      g(prefix + ".ff.net.0.proj.bias").to(dev), GEGLU_BN, return_perm=True)
             blk = SimpleNamespace(
                 ln1=norm(prefix + ".norm1"), ln2=norm(prefix + ".norm2"), ln3=norm(prefix + ".norm3"),
                 qkv=torch.cat([pack_linear(g(a1 + f".to_{n}.weight")) for n in "qkv"], 0).to(dev),
@@ -121,6 +132,12 @@ class B200UNet:
                 out2=lin(a2 + ".to_out.0"),
                 ff1=SimpleNamespace(w=w1, b=b1), ff2=lin(prefix + ".ff.net.2"))
             kv_w.extend(pack_linear(g(a2 + f".to_{n}.weight")) for n in "kv")
+            for i, n in enumerate("qkv"):
+                reg(a1 + f".to_{n}", "linear", lambda: blk.qkv, i * C, C)
+            reg(a2 + ".to_q", "linear", lambda: blk.q2, 0, C)
+            reg(a2 + ".to_k", "linear", lambda: self.kv_all, self._kv_off, C)
+            reg(a2 + ".to_v", "linear", lambda: self.kv_all, self._kv_off + C, C)
+            reg(prefix + ".ff.net.0.proj", "linear", lambda: blk.ff1.w, 0, w1.shape[0], perm)
             self._kv_off += 2 * C
             self.attn_places += [place, place]
             return blk
@@ -183,6 +200,80 @@ class B200UNet:
         # one GEMM for every ResnetBlock2D.time_emb_proj of the network
         self.temb_all = SimpleNamespace(w=torch.cat([pack_linear(w) for w in temb_w], 0).to(dev),
                                         b=torch.cat([_f32(b, dev) for b in temb_b], 0))
+
+    # ------------------------------------------------------------------ hot-swappable LoRA adapters
+    # The reference keeps three full U-Nets resident (teacher + two deep copies with a LoRA fused in,
+    # utils/loading.py:63-88,116-146). Alternative offered here: ONE packed U-Net, the base copy of the
+    # adapted matrices, and per adapter the low-rank factors pre-arranged in the packed layout. Switching adapters
+    # re-materialises  W = W_base + (alpha/r) * B.A  on the GPU: one tcgen05 GEMM per adapted module (M = C_out,
+    # N = packed C_in, K = r) whose epilogue adds the base weights (the residual is accumulated on the tensor core in
+    # fp32) and rounds to fp16 once — the same arithmetic as `loading.fuse_lora` up to fp32 summation order. The working
+    # tensors are updated in place, so captured CUDA graphs (which hold their addresses) stay valid.
+    def add_adapter(self, name, lora_weights, lora_dtype=torch.float16, alpha=8):
+        """Register a peft-format LoRA state dict (`unet.base_model.model.<module>.lora_{A,B}.weight`,
+        utils/loading.py:10-23) under `name`. A and B are first cast to `lora_dtype` as the reference does (fp16 for
+        SD1.5, utils/loading.py:68; fp32 for SDXL, :122), then rounded to the fp16 operands of the fuse GEMM."""
+        prefix = "unet.base_model.model."
+        mods = sorted({k[len(prefix):].rsplit(".lora_", 1)[0] for k in lora_weights if k.startswith(prefix)})
+        if not mods:
+            raise ValueError("add_adapter: no peft-format keys ('unet.base_model.model.*.lora_A.weight') found")
+        if not hasattr(self, "_adapters"):
+            self._adapters, self._base_copy, self._active = {}, {}, None
+        dev, packed = self.device, {}
+        for mod in mods:
+            if mod not in self._wmap:
+                raise KeyError(f"LoRA adapter for unknown module {mod}")
+            kind, getter, row0, nrows, perm = self._wmap[mod]
+            A = lora_weights[f"{prefix}{mod}.lora_A.weight"].to(lora_dtype).float().to(dev)
+            Bm = lora_weights[f"{prefix}{mod}.lora_B.weight"].to(lora_dtype).float().to(dev).flatten(1)
+            rank = A.shape[0]
+            if Bm.shape[0] != nrows:
+                raise ValueError(f"LoRA B of {mod}: {Bm.shape[0]} rows, expected {nrows}")
+            if perm is not None:
+                Bm = Bm[perm]
+            Bp = (Bm * (alpha / rank)).to(torch.float16).contiguous()                 # [C_out, r]
+            Ap = pack_conv3x3(A) if kind == "conv" else pack_linear(A)                # [r, packed C_in]
+            if Ap.shape[1] != getter().shape[1]:
+                raise ValueError(f"LoRA A of {mod}: {Ap.shape[1]} packed columns, expected {getter().shape[1]}")
+            packed[mod] = (Bp, Ap.t().contiguous())                                   # GEMM "weight" operand [N, K=r]
+            w = getter()
+            if w.data_ptr() not in self._base_copy:
+                self._base_copy[w.data_ptr()] = w.clone()
+        self._adapters[name] = packed
+
+    def set_adapter(self, name):
+        """Make adapter `name` (None = the base model) the one the packed weights contain. Launches only; no sync."""
+        if not hasattr(self, "_adapters"):
+            if name is None:
+                return
+            raise KeyError(f"no adapter '{name}' (none registered)")
+        if name == self._active:
+            return
+        if name is not None and name not in self._adapters:
+            raise KeyError(f"no adapter '{name}' (have {sorted(self._adapters)})")
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("set_adapter inside a CUDA-graph capture: activate the adapter before capturing")
+        new = self._adapters[name] if name is not None else {}
+        old = self._adapters[self._active] if self._active is not None else {}
+        with torch.cuda.device(self.device):
+            for mod in sorted(set(new) | set(old)):
+                _, getter, row0, nrows, _ = self._wmap[mod]
+                w = getter()
+                work, base = w[row0:row0 + nrows], self._base_copy[w.data_ptr()][row0:row0 + nrows]
+                if mod in new:
+                    Bp, At = new[mod]
+                    ops.linear(Bp, At, residual=base, out=work)
+                else:
+                    work.copy_(base)
+        self._active = name
+
+    @property
+    def active_adapter(self):
+        return getattr(self, "_active", None)
+
+    def adapter_view(self, name):
+        """A U-Net-like handle that runs this executor with adapter `name` active (see AdapterView)."""
+        return AdapterView(self, name)
 
     # ------------------------------------------------------------------ embeddings
     def _freqs(self, kind, dim):
@@ -380,3 +471,54 @@ class B200UNet:
         return out
 
     __call__ = forward
+
+
+class AdapterView:
+    """`pipeline.unet` of one model (teacher / forward / reverse consistency student) when several adapters share a
+    single B200UNet (`loading.load_models(..., adapters="swap")`). Every call activates its adapter first (a no-op
+    when it already is the active one), then runs the shared executor with this view's controller. Owns its own
+    CUDA-graph cache (graphs.py keys the cache by owner object); graphs captured for one view replay correctly for it
+    because the packed weights are rewritten in place."""
+
+    def __init__(self, shared, name):
+        self.__dict__["_shared"] = shared
+        self.__dict__["_name"] = name
+        self.__dict__["controller"] = None
+
+    supports_cond_only = True
+
+    def activate(self):
+        self._shared.set_adapter(self._name)
+
+    def __getattr__(self, k):           # config, device, dtype, guidance_embedding, cached_vector, attn_places, ...
+        return getattr(self.__dict__["_shared"], k)
+
+    def __setattr__(self, k, v):
+        if k in ("controller", "_icd_graphs"):
+            self.__dict__[k] = v
+        else:
+            setattr(self._shared, k, v)
+
+    def forward(self, *args, **kwargs):
+        shared = self._shared
+        if not torch.cuda.is_current_stream_capturing():
+            self.activate()
+        elif shared.active_adapter != self._name:
+            raise RuntimeError("AdapterView called inside a CUDA-graph capture with another adapter active")
+        saved = shared.controller
+        shared.controller = self.controller
+        try:
+            return shared.forward(*args, **kwargs)
+        finally:
+            shared.controller = saved
+
+    __call__ = forward
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def named_children(self):
+        return iter(())

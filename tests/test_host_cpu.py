@@ -543,3 +543,27 @@ def test_vae_oracle_small_roundtrip_shapes_and_distribution():
     assert len(pil) == 2 and pil[0].size == (64, 64)
     arr = VaeImageProcessor.postprocess(img, output_type="np")
     assert arr.shape == (2, 64, 64, 3) and arr.min() >= 0.0 and arr.max() <= 1.0
+
+
+def test_adapter_factors_land_in_the_packed_layout():
+    """Hot-swappable adapters (unet.B200UNet.add_adapter): the low-rank factors are re-arranged at registration so that
+    B'.A'^T + W_base IS the packed form of the load-time fuse (loading.fuse_lora) for every adapted module — q|k|v
+    concat, the all-layer K|V matrix, the all-ResBlock time_emb_proj matrix, GEGLU row interleave, conv tap order.
+    Checked on the host in fp32 (the GPU test runs the same contraction on the tensor cores)."""
+    from invertible_cd_b200 import arch, loading
+    from invertible_cd_b200.unet import B200UNet
+    cfg = arch.small_sd15_config()
+    sd = arch.synthetic_state_dict(cfg, seed=5)
+    lora = arch.synthetic_lora(cfg, r=8, seed=3, std=0.05)
+    net = B200UNet(cfg, sd, device="cpu")
+    fused = B200UNet(cfg, loading.fuse_lora(sd, lora, r=8), device="cpu")
+    net.add_adapter("rev", lora)
+    assert set(net._adapters["rev"]) == set(arch.lora_target_modules(cfg))
+    for mod, (Bp, At) in net._adapters["rev"].items():
+        _, getter, row0, nrows, _ = net._wmap[mod]
+        base = getter()[row0:row0 + nrows].float()
+        want = fused._wmap[mod][1]()[row0:row0 + nrows].float()
+        got = (Bp.float() @ At.float().t() + base).half().float()
+        ulp = torch.clamp(want.abs(), min=6.1e-5) * 2.0 ** -10
+        assert ((got - want).abs() / ulp).max().item() <= 1.01, mod
+        assert not torch.equal(want, base.half().float()), mod

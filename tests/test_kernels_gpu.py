@@ -429,6 +429,31 @@ def test_attention_fused_cross_with_capture(ops, B, H, Nq, D):
     assert probs[..., Nk:].abs().max() == 0
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk,D,stats", [(8, 8, 4096, 77, 40, True),     # 7-tile runs per CTA, last run shorter
+                                               (10, 8, 1100, 77, 64, False),   # 3-tile runs, partial last query tile
+                                               (4, 20, 1024, 77, 64, False), (8, 8, 1024, 77, 80, True),
+                                               (8, 8, 256, 77, 160, False), (2, 8, 64, 77, 160, True),
+                                               (3, 5, 500, 80, 40, False), (3, 5, 130, 9, 64, True)])
+def test_attention_short_context_kernel(ops, B, H, Nq, Nk, D, stats):
+    """attention_smallkv_kernel (N_kv <= 80: the text context): one CTA walks a run of query tiles with K/V resident,
+    exact one-pass softmax, probabilities normalised before P.V. Without capture; optional statistics export."""
+    q = _rand(B * Nq, H * D, seed=73) * 2
+    kv = _rand(B * Nk, 2 * H * D, seed=74) * 2
+    k, v = kv[:, :H * D], kv[:, H * D:]
+    scale = D ** -0.5
+    st = torch.full((B * H, Nq, 2), float("nan"), device="cuda") if stats else None
+    out = ops.attention(q, k, v, B, H, Nq, Nk, D, scale, stats_out=st)
+    ref_o, ref_p = _attn_ref(q, k, v, B, H, Nq, Nk, D, scale)
+    _close(out, ref_o, rtol=2e-3, atol=2e-3, what="short-context out")
+    if stats:
+        sc = (q.float().reshape(B, Nq, H, D).permute(0, 2, 1, 3) @
+              k.float().reshape(B, Nk, H, D).permute(0, 2, 3, 1)) * scale
+        m = sc.max(-1).values.reshape(B * H, Nq)
+        l = torch.exp(sc - sc.max(-1, keepdim=True).values).sum(-1).reshape(B * H, Nq)
+        torch.testing.assert_close(st[..., 0], m * 1.4426950408889634, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(st[..., 1], 1.0 / l, rtol=2e-3, atol=1e-6)
+
+
 @pytest.mark.parametrize("Nq,Nk,ldp", [(200, 64, 64), (200, 128, 128), (77, 100, 104), (130, 13, 16), (96, 77, 77),
                                        (300, 77, 144)])
 def test_attention_capture_ragged(ops, Nq, Nk, ldp):

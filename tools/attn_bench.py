@@ -18,15 +18,17 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", type=int, default=-1)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--no-capture", action="store_true", help="cross-attention shapes without the probability write-out")
+    ap.add_argument("--cross-only", action="store_true")
     a = ap.parse_args()
     for i, (B, H, Nq, Nk, D) in enumerate(SHAPES):
-        if a.only >= 0 and i != a.only:
+        if (a.only >= 0 and i != a.only) or (a.cross_only and Nk > 128):
             continue
         q = torch.randn(B * Nq, H * D, device="cuda").half()
         k = torch.randn(B * Nk, H * D, device="cuda").half()
         v = torch.randn(B * Nk, H * D, device="cuda").half()
         out = torch.empty_like(q)
-        probs = torch.empty(B * H, Nq, (Nk + 7) // 8 * 8, device="cuda", dtype=torch.float16) if Nk <= 128 else None
+        probs = torch.empty(B * H, Nq, (Nk + 7) // 8 * 8, device="cuda", dtype=torch.float16) if Nk <= 128 and not a.no_capture else None
         fn = lambda: ops.attention(q, k, v, B, H, Nq, Nk, D, D ** -0.5, out=out, probs_out=probs)
         us = time_us(fn, a.iters)
         fl = 4.0 * B * H * Nq * Nk * D
