@@ -161,6 +161,59 @@ int icd_consistency_update(const float* eps, const float* x, float* out, long lo
                            const float* alpha_t, const float* sigma_t, const float* alpha_s, const float* sigma_s,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32 validation path (ABI 3). `load_models(dtype='fp32')` — the dtype the reference runs SD1.5 editing in
+ * (running/sd1.5/launch_editing_iCD_sd1.5.sh:38, utils/loading.py:38-41) — executes the SAME U-Net executor on these
+ * kernels: fp32 operands and activations, contractions on the FMA pipe with fp32 accumulation, same packed layouts
+ * and epilogue semantics as the fp16 entry points above. A correctness mode (element-wise agreement with the fp32
+ * oracle), not a fast path. Each call replaces the fp32 torch op the fp16 entry point of the same name replaces.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct IcdSgemm {
+  /* out[z][m][n] = alpha * sum_k A[z][m][k] * Bm[z][n][k] (+ bias[n]) (+ rowvec[m / rows_per_img][n]) (+ residual) */
+  const float* a0;       /* A = [a0 | a1] along K (per filter tap when conv = 1) */
+  const float* a1;
+  int C0, C1;            /* columns (channels) of a0 / a1 */
+  long long a0_ld, a1_ld;
+  int conv;              /* 0: plain rows; 1: implicit 3x3 / pad 1 / stride 1 over NHWC images, K = (tap, channel) */
+  int B, H, W;           /* conv: image geometry, M = B*H*W */
+  int w_tap_ld;          /* conv: weight columns per filter tap (the packed, padded C_in) */
+  const float* b;        /* weights / second operand */
+  long long b_ld;
+  int b_kn;              /* 0: b is [N][K] (K contiguous); 1: b is [K][N] (P.V with V as it lies in memory) */
+  int M, N, K;           /* K is implied (C0 + C1, or 9 * (C0 + C1)) and ignored on input */
+  int Z, ZH;             /* batch index z -> (zb, zh) = (z / ZH, z % ZH) */
+  long long a_zb, a_zh, b_zb, b_zh, c_zb, c_zh, r_zb, r_zh;   /* element offsets per batch index (a0, b, out, residual) */
+  float alpha;
+  const float* bias;     /* [N] or NULL */
+  const float* rowvec;   /* [images][ldv] added to every row of image m / rows_per_img, or NULL */
+  int rows_per_img;
+  long long ldv;
+  const float* residual; /* [M][ldr] or NULL */
+  long long ldr;
+  float* out;
+  long long ldc;
+  int vec;               /* internal (set by the library) */
+} IcdSgemm;
+int icd_sgemm_f32(const IcdSgemm* g, void* stream);
+int icd_groupnorm_f32(const float* x0, int C0, const float* x1, int C1, float* y, int B, int HW, int groups, float eps,
+                      const float* gamma, const float* beta, int silu, void* stream);
+int icd_layernorm_f32(const float* x, float* y, int rows, int C, float eps, const float* gamma, const float* beta,
+                      void* stream);
+/* in place over the first `cols` entries of `rows` rows of stride ld; entries [cols, ld) become 0 */
+int icd_softmax_f32(float* x, long long rows, int cols, long long ld, void* stream);
+int icd_silu_f32(const float* x, float* y, long long n, void* stream);
+/* y[m][j] = h * gelu(g) of a [M][2F] projection whose rows are interleaved per bn-wide tile (packing.pack_geglu) */
+int icd_geglu_f32(const float* x, float* y, long long M, int F, int bn, void* stream);
+int icd_upsample2x_f32(const float* x, float* y, int B, int H, int W, int C, void* stream);
+int icd_im2col_s2_f32(const float* x, float* y, int B, int H, int W, int C, void* stream);
+/* NCHW -> NHWC with channels zero-padded to Cpad; NHWC (row stride ld, leading C channels) -> NCHW */
+int icd_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int HW, int Cpad, void* stream);
+int icd_nhwc_to_nchw_f32(const float* x, long long ld, float* y, int B, int C, int HW, void* stream);
+/* y[r] = sin_first ? [sin a | cos a] : [cos a | sin a], a = (v[r] * scale) * freqs[k]: Timesteps (scale 1, cos first)
+ * and guidance_scale_embedding (scale 1000, sin first; utils/generation.py:96-122) with fp32 output */
+int icd_sincos_embedding_f32(const float* v, const float* freqs, float* y, int n, int dim, float scale, int sin_first,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

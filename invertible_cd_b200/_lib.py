@@ -14,6 +14,10 @@ EXPORTED_SYMBOLS = [
     "icd_last_error", "icd_device_info", "icd_abi_version", "icd_set_pdl", "icd_gemm", "icd_gemm_pick_bn", "icd_attention", "icd_attention_ex",
     "icd_groupnorm", "icd_groupnorm_launches", "icd_layernorm", "icd_softmax", "icd_softmax_causal", "icd_act", "icd_embed_tokens", "icd_upsample2x", "icd_im2col_s2", "icd_im2col_s2_pad", "icd_latent_to_nhwc",
     "icd_timestep_embedding", "icd_guidance_embedding", "icd_silu", "icd_add", "icd_consistency_update",
+    # fp32 validation path (ABI 3)
+    "icd_sgemm_f32", "icd_groupnorm_f32", "icd_layernorm_f32", "icd_softmax_f32", "icd_silu_f32", "icd_geglu_f32",
+    "icd_upsample2x_f32", "icd_im2col_s2_f32", "icd_nchw_to_nhwc_f32", "icd_nhwc_to_nchw_f32",
+    "icd_sincos_embedding_f32",
 ]
 
 
@@ -34,6 +38,21 @@ class IcdGemm(C.Structure):
         ("upd_x", C.c_void_p), ("upd_out", C.c_void_p),
         ("alpha_t", C.c_float), ("sigma_t", C.c_float), ("alpha_s", C.c_float), ("sigma_s", C.c_float),
         ("exp_stats", C.c_void_p),
+    ]
+
+
+class IcdSgemm(C.Structure):
+    """Mirror of `struct IcdSgemm` (include/icd_b200.h): the fp32 validation contraction."""
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p), ("C0", C.c_int), ("C1", C.c_int), ("a0_ld", C.c_longlong),
+        ("a1_ld", C.c_longlong), ("conv", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("w_tap_ld", C.c_int), ("b", C.c_void_p), ("b_ld", C.c_longlong), ("b_kn", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("Z", C.c_int), ("ZH", C.c_int),
+        ("a_zb", C.c_longlong), ("a_zh", C.c_longlong), ("b_zb", C.c_longlong), ("b_zh", C.c_longlong),
+        ("c_zb", C.c_longlong), ("c_zh", C.c_longlong), ("r_zb", C.c_longlong), ("r_zh", C.c_longlong),
+        ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rows_per_img", C.c_int),
+        ("ldv", C.c_longlong), ("residual", C.c_void_p), ("ldr", C.c_longlong), ("out", C.c_void_p),
+        ("ldc", C.c_longlong), ("vec", C.c_int),
     ]
 
 
@@ -82,6 +101,18 @@ def load():
     lib.icd_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     lib.icd_consistency_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+    lib.icd_sgemm_f32.argtypes = [C.POINTER(IcdSgemm), P]
+    lib.icd_groupnorm_f32.argtypes = [P, I, P, I, P, I, I, I, F, P, P, I, P]
+    lib.icd_layernorm_f32.argtypes = [P, P, I, I, F, P, P, P]
+    lib.icd_softmax_f32.argtypes = [P, L, I, L, P]
+    lib.icd_silu_f32.argtypes = [P, P, L, P]
+    lib.icd_geglu_f32.argtypes = [P, P, L, I, I, P]
+    lib.icd_upsample2x_f32.argtypes = [P, P, I, I, I, I, P]
+    lib.icd_im2col_s2_f32.argtypes = [P, P, I, I, I, I, P]
+    lib.icd_nchw_to_nhwc_f32.argtypes = [P, P, I, I, I, I, P]
+    lib.icd_nhwc_to_nchw_f32.argtypes = [P, L, P, I, I, I, P]
+    lib.icd_sincos_embedding_f32.argtypes = [P, P, P, I, I, F, I, P]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name != "icd_last_error":

@@ -48,7 +48,7 @@ int check_launch(const char* what) {
 }  // namespace icd
 
 extern "C" const char* icd_last_error(void) { return icd::g_err.c_str(); }
-extern "C" int icd_abi_version(void) { return 2; }   // 2: IcdGemm.exp_stats, icd_attention_ex, VAE / CLIP helper kernels
+extern "C" int icd_abi_version(void) { return 3; }   // 2: IcdGemm.exp_stats, icd_attention_ex, VAE / CLIP helper kernels; 3: fp32 validation path (icd_*_f32)
 extern "C" int icd_set_pdl(int enabled) {
   const int prev = icd::pdl_enabled() ? 1 : 0;
   icd::g_pdl = enabled ? 1 : 0;

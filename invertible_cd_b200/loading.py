@@ -242,13 +242,16 @@ def _students_swap(teacher_pipe, shared, cfg, ckpts, r, device, lora_dtype):
 def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, w_embed_dim=0,
                 teacher_checkpoint=None, dtype='fp32', adapters=None):
     """-> (ldm_stable, reverse_cons_model, forward_cons_model), as utils/loading.py:27-90.
-    `dtype` selects the dtype of the latents the loop carries ('fp32'/'fp16'); the U-Net kernels always compute in
-    fp16 with fp32 accumulation (documented deviation: the reference's fp32 editing mode runs fp32 cuBLAS/cuDNN).
+    `dtype`: 'fp16' = the tcgen05 path (fp16 operands / activations, fp32 accumulation); 'fp32' = fp32 latents AND the
+    fp32 validation kernels (ops_f32: fp32 operands, activations and accumulation on the FMA pipe — the reference's
+    fp32 editing mode, running/sd1.5/launch_editing_iCD_sd1.5.sh:38; ~20x slower than fp16). ICD_FP32_KERNELS=0 keeps
+    the fp16 kernels under fp32 latents (the round-1 behaviour).
     `adapters` (extension; default from ICD_LORA_ADAPTERS, else 'resident'): 'resident' keeps three packed U-Nets as
     the reference keeps three pipelines; 'swap' keeps ONE plus the low-rank factors and re-fuses on the GPU when a
     different model is called (unet.B200UNet.set_adapter)."""
     mode = _adapter_mode(adapters)
     tdtype = torch.float32 if dtype == 'fp32' else torch.float16
+    precision = "fp32" if dtype == 'fp32' and os.environ.get("ICD_FP32_KERNELS", "1") != "0" else "fp16"
     scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
                               set_alpha_to_one=False)
     cfg, sd, text = _unet_source(model_id, w_embed_dim, is_xl=False, device=device)
@@ -261,7 +264,7 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
             print('PROVIDE TEACHER')
     _validate(cfg, sd)
     text_encoder = text.get("text_encoder")
-    ldm_stable = ICDPipeline(B200UNet(cfg, sd, device), scheduler, _vae_source(model_id, device, False),
+    ldm_stable = ICDPipeline(B200UNet(cfg, sd, device, precision), scheduler, _vae_source(model_id, device, False),
                              text.get("tokenizer"), text_encoder, device, tdtype)
     if mode == "swap":
         rev, fwd = _students_swap(ldm_stable, ldm_stable.unet, cfg,
@@ -275,7 +278,7 @@ def load_models(model_id, device, reverse_checkpoint, forward_checkpoint, r=64, 
             continue
         print(f'{name} CD is loading from {ckpt if isinstance(ckpt, str) else "<state dict>"}')
         fused = fuse_lora(sd, _lora_source(ckpt, cfg, r, device), r=r, lora_dtype=torch.float16)
-        students.append(ldm_stable.clone_with_unet(B200UNet(cfg, fused, device)))
+        students.append(ldm_stable.clone_with_unet(B200UNet(cfg, fused, device, precision)))
     return ldm_stable, students[0], students[1]
 
 

@@ -20,8 +20,8 @@ from types import SimpleNamespace
 
 import torch
 
-from . import ops
-from .packing import pack_conv3x3, pack_geglu, pack_linear
+from . import ops, ops_f32
+from . import packing
 
 GEGLU_BN = 256
 
@@ -44,7 +44,15 @@ def _f32(t, dev):
 class B200UNet:
     """Packed weights + forward of one U-Net (teacher, forward-consistency or reverse-consistency model)."""
 
-    def __init__(self, config, state_dict, device="cuda"):
+    def __init__(self, config, state_dict, device="cuda", precision="fp16"):
+        """`precision`: 'fp16' = the tcgen05 path (fp16 operands and activations, fp32 accumulation);
+        'fp32' = the validation path (ops_f32: fp32 everywhere, FMA-pipe contractions) that
+        `load_models(dtype='fp32')` selects, as the reference's fp32 mode (utils/loading.py:38-41)."""
+        if precision not in ("fp16", "fp32"):
+            raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        self.ops = ops_f32 if precision == "fp32" else ops
+        self.act_dtype = torch.float32 if precision == "fp32" else torch.float16
         self.config = config if not isinstance(config, dict) else SimpleNamespace(**config)
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
@@ -59,7 +67,7 @@ class B200UNet:
     # ------------------------------------------------------------------ reference-visible attributes
     @property
     def dtype(self):
-        return torch.float16            # compute dtype of the kernels (utils/generation.py:241 casts inputs to it)
+        return self.act_dtype           # compute dtype of the kernels (utils/generation.py:241 casts inputs to it)
 
     @property
     def in_channels(self):
@@ -80,8 +88,11 @@ class B200UNet:
 
     # ------------------------------------------------------------------ packing
     def _pack(self, sd):
-        cfg, dev = self.config, self.device
+        cfg, dev, wd = self.config, self.device, self.act_dtype
         g = lambda k: sd[k]
+        pack_conv3x3 = lambda w: packing.pack_conv3x3(w, wd)
+        pack_linear = lambda w: packing.pack_linear(w, wd)
+        pack_geglu = lambda w, b, bn, return_perm=False: packing.pack_geglu(w, b, bn, return_perm, wd)
         boc = list(cfg.block_out_channels)
         self.temb_ch = boc[0] * 4
         temb_w, temb_b = [], []
@@ -231,8 +242,8 @@ class B200UNet:
                 raise ValueError(f"LoRA B of {mod}: {Bm.shape[0]} rows, expected {nrows}")
             if perm is not None:
                 Bm = Bm[perm]
-            Bp = (Bm * (alpha / rank)).to(torch.float16).contiguous()                 # [C_out, r]
-            Ap = pack_conv3x3(A) if kind == "conv" else pack_linear(A)                # [r, packed C_in]
+            Bp = (Bm * (alpha / rank)).to(self.act_dtype).contiguous()                # [C_out, r]
+            Ap = (packing.pack_conv3x3 if kind == "conv" else packing.pack_linear)(A, self.act_dtype)   # [r, packed C_in]
             if Ap.shape[1] != getter().shape[1]:
                 raise ValueError(f"LoRA A of {mod}: {Ap.shape[1]} packed columns, expected {getter().shape[1]}")
             packed[mod] = (Bp, Ap.t().contiguous())                                   # GEMM "weight" operand [N, K=r]
@@ -262,7 +273,7 @@ class B200UNet:
                 work, base = w[row0:row0 + nrows], self._base_copy[w.data_ptr()][row0:row0 + nrows]
                 if mod in new:
                     Bp, At = new[mod]
-                    ops.linear(Bp, At, residual=base, out=work)
+                    self.ops.linear(Bp, At, residual=base, out=work)
                 else:
                     work.copy_(base)
         self._active = name
@@ -298,10 +309,10 @@ class B200UNet:
     def guidance_embedding(self, w, dim=512):
         """w: fp32 [rows] device tensor -> fp16 [rows, dim] (utils/generation.py:96-122)."""
         with torch.cuda.device(self.device):
-            return ops.guidance_embedding(w, self._freqs("w", dim), dim)
+            return self.ops.guidance_embedding(w, self._freqs("w", dim), dim)
 
     def _time_embed(self, rows, timestep, timestep_cond, added):
-        dev = self.device
+        dev, ops = self.device, self.ops
         if torch.is_tensor(timestep):
             t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
             if t.numel() == 1:
@@ -314,12 +325,12 @@ class B200UNet:
         if timestep_cond is not None:
             if self.cond_proj is None:
                 raise ValueError("timestep_cond given but the model has no time_cond_proj_dim")
-            cond = timestep_cond.to(device=dev, dtype=torch.float16).contiguous()
+            cond = timestep_cond.to(device=dev, dtype=self.act_dtype).contiguous()
             t_emb = ops.linear(cond, self.cond_proj, residual=t_emb)        # t_emb + cond_proj(w_emb)
         h = ops.silu(ops.linear(t_emb, self.time_lin1.w, bias=self.time_lin1.b))
         emb = ops.linear(h, self.time_lin2.w, bias=self.time_lin2.b)
         if self.is_xl:
-            text_embeds = added["text_embeds"].to(device=dev, dtype=torch.float16)
+            text_embeds = added["text_embeds"].to(device=dev, dtype=self.act_dtype)
             time_ids = added["time_ids"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
             d = self.config.addition_time_embed_dim
             tid = ops.timestep_embedding(time_ids, self._freqs("t", d), d).reshape(rows, -1)
@@ -332,7 +343,7 @@ class B200UNet:
     # ------------------------------------------------------------------ blocks
     def _res(self, r, x0, x1, B, H, W):
         """ResnetBlock2D over channels-last tokens; (x0 | x1) is the virtual channel concat of the skip."""
-        ws = self._gn_ws
+        ws, ops = self._gn_ws, self.ops
         h = ops.groupnorm(x0, B, H * W, r.norm1.g, r.norm1.b, 1e-5, True, ws, x1=x1)
         temb = self._temb[:, r.temb_off:r.temb_off + r.cout]
         h = ops.conv3x3(h, r.conv1.w, B, H, W, bias=r.conv1.b, rowvec=temb)
@@ -346,7 +357,7 @@ class B200UNet:
     def _attention(self, q, k, v, B, heads, Nq, Nk, d, is_cross, place):
         """Attention core + the p2p controller protocol (utils/p2p.py:335-338)."""
         scale = d ** -0.5
-        ctrl = self.controller
+        ctrl, ops, fp32 = self.controller, self.ops, self.precision == "fp32"
         req = "none" if ctrl is None else ctrl.probs_request(is_cross, place, Nq, Nk)
         if req == "none":
             out = ops.attention(q, k, v, B, heads, Nq, Nk, d, scale)
@@ -356,11 +367,11 @@ class B200UNet:
         ldp = (Nk + 7) // 8 * 8
         if req == "read" and Nk <= 128:
             # the kernel writes every padded row completely (pad columns are zero): no memset needed
-            probs = torch.empty((B * heads, Nq, ldp), device=q.device, dtype=torch.float16)
+            probs = torch.empty((B * heads, Nq, ldp), device=q.device, dtype=self.act_dtype)
             out = ops.attention(q, k, v, B, heads, Nq, Nk, d, scale, probs_out=probs)
             ctrl.call_rows(probs[..., :Nk], is_cross, place, self._cond_only)
             return out
-        if req == "read" and Nk % 8 == 0:
+        if req == "read" and Nk % 8 == 0 and not fp32:
             # larger read-only maps (self-attention, N_q <= 1024): the fused kernel produces the output and the
             # online-softmax statistics; one more pass over Q.K^T writes the normalised probabilities directly
             stats = torch.empty((B * heads, Nq, 2), device=q.device, dtype=torch.float32)
@@ -370,19 +381,19 @@ class B200UNet:
             ctrl.call_rows(probs, is_cross, place, self._cond_only)
             return out
         # explicit probabilities: scores GEMM -> softmax -> controller (may edit in place) -> P.V GEMM
-        probs = torch.zeros((B * heads, Nq, ldp), device=q.device, dtype=torch.float16)
+        probs = torch.zeros((B * heads, Nq, ldp), device=q.device, dtype=self.act_dtype)
         ops.attn_scores(q, k, B, heads, Nq, Nk, d, scale, probs)
         ops.softmax_(probs, Nk)
         view = probs[..., :Nk]
         edited = ctrl.call_rows(view, is_cross, place, self._cond_only)
         if edited.data_ptr() != view.data_ptr() or edited.stride() != view.stride():
             view.copy_(edited)           # controller returned a new tensor: bring it back into the padded buffer
-        out = torch.empty((B * Nq, heads * d), device=q.device, dtype=torch.float16)
+        out = torch.empty((B * Nq, heads * d), device=q.device, dtype=self.act_dtype)
         ops.attn_pv(probs, v, B, heads, Nq, Nk, d, out)
         return out
 
     def _tfm(self, t, x, ctx, B, HW, place):
-        C, heads, d = t.C, t.heads, t.d
+        C, heads, d, ops = t.C, t.heads, t.d, self.ops
         n_ctx = ctx.shape[0] // B
         h = ops.groupnorm(x, B, HW, t.norm.g, t.norm.b, 1e-6, False, self._gn_ws)
         h = ops.linear(h, t.proj_in.w, bias=t.proj_in.b)
@@ -415,10 +426,10 @@ class B200UNet:
         `cond_only`: the rows are the conditional half only (controller sees them all).
         `update`: optional (x_t fp32 NCHW, alpha_t, sigma_t, alpha_s, sigma_s): fuse predicted_origin into the
         conv_out epilogue; the next latent is returned as out["next_sample"]."""
-        dev = self.device
+        dev, ops = self.device, self.ops
         rows, _, H, W = sample.shape
         lat = sample.to(device=dev, dtype=torch.float32).contiguous()
-        ctx = encoder_hidden_states.to(device=dev, dtype=torch.float16)
+        ctx = encoder_hidden_states.to(device=dev, dtype=self.act_dtype)
         if ctx.shape[0] != rows:
             raise ValueError(f"encoder_hidden_states rows {ctx.shape[0]} != sample rows {rows}")
         ctx = ctx.reshape(rows * ctx.shape[1], ctx.shape[2]).contiguous()

@@ -456,9 +456,9 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.icd_abi_version() == 2
+    assert lib.icd_abi_version() == 3
     import ctypes
-    assert ctypes.sizeof(_lib.IcdGemm) == 312
+    assert ctypes.sizeof(_lib.IcdGemm) == 312 and ctypes.sizeof(_lib.IcdSgemm) == 248
 
 
 def test_product_fails_loudly_without_the_extension(monkeypatch):
