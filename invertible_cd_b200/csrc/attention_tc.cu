@@ -47,13 +47,15 @@ struct AttnParams {
   __half* probs;      // optional [B*H][Nq][probs_ld]
   long long probs_ld;
   float* stats;       // optional [B*H][Nq][2]: (m_run * scale_log2e, 1 / l) of the online softmax
+  int speculate;      // exponentials of a tile start before its maximum is known (see the softmax loop)
 #ifdef ICD_ATTN_PROFILE
   long long* prof;    // [MT][8] phase cycle counters of one softmax warp per query tile (debug builds only)
 #endif
 };
 
 // Phase timing of one softmax warp (debug builds: make PROF=1): cycles spent per key tile in
-//   0 wait S | 1 tcgen05.ld | 2 max + rescale decision | 3 (unused) | 4 exponentials | 5 tcgen05.st + arrive
+//   0 wait S | 1 tcgen05.ld (first 32 scores) | 2 max + rescale decision | 3 second load / speculation redo |
+//   4 exponentials (speculative tiles: incl. the wait for the second 32 scores) | 5 tcgen05.st + arrive
 #ifdef ICD_ATTN_PROFILE
 #define ICD_PROF_DECL long long pt_[7] = {0, 0, 0, 0, 0, 0, 0}, pc_ = clock64();
 #define ICD_PROF_MARK(k) { const long long n_ = clock64(); pt_[k] += n_ - pc_; pc_ = n_; }
@@ -318,10 +320,62 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       ICD_PROF_MARK(0)
       const int valid = min(BKV, p.Nk - j * BKV);
       float s[64];
+      auto use_poly = [](int idx) constexpr {
+        const int r = idx & 7;
+        return (POLY >= 1 && r == 6) || (POLY >= 2 && r == 3) || (POLY >= 3 && r == 1) || (POLY >= 4 && r == 4);
+      };
       tmem_ld32(t0 + bsel * BKV, s);
-      tmem_ld32(t0 + bsel * BKV + 32, s + 32);
       tmem_ld_wait();
       ICD_PROF_MARK(1)
+      if (p.speculate && j > 0 && valid == BKV) {
+        // Speculative tile (every full tile but the first): the lazily-updated reference maximum m_run almost never
+        // moves, so the exponentials start from the first 32 scores right away with the CURRENT m_run — no wait for
+        // the tile maximum, and the load of the other 32 scores is in flight meanwhile. The maximum is tracked on the
+        // side; if any row of the warp did move (warp-uniform check), the tile is redone on the regular path below
+        // from the scores still in registers. Identical arithmetic, hence identical results.
+        tmem_ld32(t0 + bsel * BKV + 32, s + 32);
+        const float m_sc = m_run * p.scale_log2e;
+        uint32_t pk[32];
+        float mxa = fmaxf(s[0], s[1]), mxb = fmaxf(s[2], s[3]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x0 = fmaf(s[2 * i], p.scale_log2e, -m_sc), x1 = fmaf(s[2 * i + 1], p.scale_log2e, -m_sc);
+          const float e0 = use_poly(2 * i) ? exp2_poly(x0) : exp2_mufu(x0);
+          const float e1 = use_poly(2 * i + 1) ? exp2_poly(x1) : exp2_mufu(x1);
+          const __half2 e = __floats2half2_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&e);
+          if (i >= 2) {
+            if (i & 1) mxb = fmaxf(mxb, fmaxf(s[2 * i], s[2 * i + 1]));
+            else mxa = fmaxf(mxa, fmaxf(s[2 * i], s[2 * i + 1]));
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 16; i < 32; ++i) {
+          const float x0 = fmaf(s[2 * i], p.scale_log2e, -m_sc), x1 = fmaf(s[2 * i + 1], p.scale_log2e, -m_sc);
+          const float e0 = use_poly(2 * i) ? exp2_poly(x0) : exp2_mufu(x0);
+          const float e1 = use_poly(2 * i + 1) ? exp2_poly(x1) : exp2_mufu(x1);
+          const __half2 e = __floats2half2_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&e);
+          if (i & 1) mxb = fmaxf(mxb, fmaxf(s[2 * i], s[2 * i + 1]));
+          else mxa = fmaxf(mxa, fmaxf(s[2 * i], s[2 * i + 1]));
+        }
+        const bool moved_spec = (fmaxf(mxa, mxb) - m_run) * p.scale_log2e > 8.0f;
+        if (!__any_sync(0xffffffffu, moved_spec)) {
+          tmem_st16_u32(t0 + bsel * BKV, pk);
+          tmem_st16_u32(t0 + bsel * BKV + 16, pk + 16);
+          ICD_PROF_MARK(4)
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full_m[bsel]);
+          ICD_PROF_MARK(5)
+          continue;
+        }
+      } else {
+        tmem_ld32(t0 + bsel * BKV + 32, s + 32);
+        tmem_ld_wait();
+      }
+      ICD_PROF_MARK(3)
       if (valid < BKV) {                    // warp-uniform: only the last K/V tile can be partial
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -363,14 +417,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       const float m_scaled = m_run * p.scale_log2e;
       ICD_PROF_MARK(2)
-      ICD_PROF_MARK(3)
       // p = exp2(s*scale*log2e - m), packed to half2 and written over the first 32 columns of S[bsel] (this thread's
       // lane only; all 64 scores are already in registers). POLY of every 8 exponentials take the FMA-pipe
       // polynomial, spread out so that both instruction streams interleave.
-      auto use_poly = [](int idx) constexpr {
-        const int r = idx & 7;
-        return (POLY >= 1 && r == 6) || (POLY >= 2 && r == 3) || (POLY >= 3 && r == 1) || (POLY >= 4 && r == 4);
-      };
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -527,7 +576,7 @@ static long long* g_prof_buf_last = nullptr;
 extern "C" void icd_attention_prof_dump(int n_kv) {
   cudaDeviceSynchronize();
   if (g_prof_buf_last == nullptr) return;
-  const char* names[7] = {"wait S", "tcgen05.ld", "max+decide", "-", "exponentials", "st+arrive", "loop"};
+  const char* names[7] = {"wait S", "ld first half", "max+decide", "ld rest/redo", "exponentials", "st+arrive", "loop"};
   for (int m = 0; m < 2; ++m) {
     printf("  tile %d cycles/key-tile:", m);
     for (int k = 0; k < 7; ++k) printf("  %s %.0f", names[k], double(g_prof_buf_last[m * 8 + k]) / n_kv);
@@ -580,6 +629,8 @@ extern "C" int icd_attention_ex(const void* q, const void* k, const void* v, voi
   p.probs = reinterpret_cast<__half*>(probs_out);
   p.probs_ld = probs_ld;
   p.stats = stats_out;
+  static const int spec_env = [] { const char* e = getenv("ICD_ATTN_SPEC"); return e ? atoi(e) : 1; }();
+  p.speculate = spec_env;
 #ifdef ICD_ATTN_PROFILE
   static long long* prof_buf = nullptr;
   if (prof_buf == nullptr) cudaMallocManaged(&prof_buf, 16 * sizeof(long long));
@@ -588,8 +639,8 @@ extern "C" int icd_attention_ex(const void* q, const void* k, const void* v, voi
   for (int i = 0; i < 16; ++i) prof_buf[i] = 0;
 #endif
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Tuning knobs, fixed per head dim from the sweep in profiles/README.md (r1h); the environment overrides are for
-  // re-running that sweep: ICD_ATTN_POLY = exponentials per 8 on the FMA pipe (0, 2, 3), ICD_ATTN_MT = query tiles
+  // Tuning knobs, fixed per head dim from the sweeps in profiles/README.md (r1h; r2_c with the speculative softmax,
+  // where the MUFU-only variant wins for every head dim); the environment overrides are for re-running the sweeps: ICD_ATTN_POLY = exponentials per 8 on the FMA pipe (0, 2, 3), ICD_ATTN_MT = query tiles
   // per CTA (1, 2; 2 only for d <= 64).
   static const int poly_env = [] { const char* e = getenv("ICD_ATTN_POLY"); return e ? atoi(e) : -1; }();
   static const int mt_env = [] { const char* e = getenv("ICD_ATTN_MT"); return e ? atoi(e) : -1; }();
@@ -602,12 +653,12 @@ extern "C" int icd_attention_ex(const void* q, const void* k, const void* v, voi
   switch (D) {
     case 40:   // self-attention (long K/V stream): two query tiles per CTA; cross-attention: more, smaller CTAs
       if ((mt_env >= 0 ? mt_env : (Nk > 128 ? 2 : 1)) == 2) { ICD_ATTN_POLY_SWITCH(40, 2, 0) }
-      ICD_ATTN_POLY_SWITCH(40, 1, 3)
+      ICD_ATTN_POLY_SWITCH(40, 1, 0)
     case 64:
-      if ((mt_env >= 0 ? mt_env : 1) == 2) { ICD_ATTN_POLY_SWITCH(64, 2, 3) }
-      ICD_ATTN_POLY_SWITCH(64, 1, 3)
-    case 80: ICD_ATTN_POLY_SWITCH(80, 1, 3)
-    case 160: ICD_ATTN_POLY_SWITCH(160, 1, 3)
+      if ((mt_env >= 0 ? mt_env : 1) == 2) { ICD_ATTN_POLY_SWITCH(64, 2, 0) }
+      ICD_ATTN_POLY_SWITCH(64, 1, 0)
+    case 80: ICD_ATTN_POLY_SWITCH(80, 1, 0)
+    case 160: ICD_ATTN_POLY_SWITCH(160, 1, 0)
     default: return set_error("icd_attention: unsupported head dim (40, 64, 80, 160)");
   }
 #undef ICD_ATTN_POLY_SWITCH
