@@ -576,7 +576,8 @@ def measure_small_batch(device, iters=10):
       b1_generation  4-step reverse generation of ONE prompt (1 U-Net row; the loop replays from the library's graph cache)
       cfg2_edit      forward-consistency inversion of one latent (4 steps, w = 0) followed by the 4-step reverse edit
                      of [source, edited] prompts with an AttentionRefine + LocalBlend controller (2 conditional rows ==
-                     the reference's 4-row U-Net batch); edit controllers run eagerly (stateful Python, graphs.py)."""
+                     the reference's 4-row U-Net batch); the edit loop replays from the graph cache too (the controller's per-edit
+                     tensors are graph inputs, graphs.py) — a new controller object is built for every edit, as a user would."""
     from invertible_cd_b200 import generation, inversion, p2p
     wl = WORKLOADS["sd15"]
     ldm, rev, solver = build_ours(wl, device)
@@ -626,7 +627,7 @@ def measure_small_batch(device, iters=10):
         ms = timed(edit)
         out["cfg2_edit"] = {"ms_per_edit": ms, "value": 1e3 / ms, "unit": "edits/s",
                             "what": "BASELINE configs[2] for one image: 4-step forward inversion (w=0, graph cache) + 4-step "
-                                    "reverse edit of [source, edit] with AttentionRefine + LocalBlend (eager), latents in / "
+                                    "reverse edit of [source, edit] with AttentionRefine + LocalBlend (graph cache; a new controller per edit), latents in / "
                                     "latents out, host inputs"}
     except Exception as e:
         out["cfg2_edit"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}

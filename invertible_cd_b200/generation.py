@@ -377,9 +377,10 @@ class Generator:
         key = ("sd15", tuple(latent.shape), latent.dtype, tuple(self.context.shape), self.context.dtype,
                ts, bs, sig, tuple(sorted((k, float(v) if isinstance(v, (int, float)) else v) for k, v in kw.items())))
         solver = self
+        ctrl_tensors = graphs.controller_tensors(attn_ctrl)     # per-edit tensors of an edit controller: graph inputs
 
-        def body(lat, ctx):
-            proto = graphs.proto_controller(attn_ctrl)
+        def body(lat, ctx, *ctrl_static):
+            proto = graphs.proto_controller(attn_ctrl, ctrl_static)
             saved_ctrl, saved_ctx = unet.controller, solver.context
             unet.controller, solver.context = proto, ctx
             try:
@@ -389,7 +390,7 @@ class Generator:
             return outs, proto
 
         with torch.cuda.device(latent.device):
-            outs, proto = graphs.run(unet, key, [latent, self.context], body)
+            outs, proto = graphs.run(unet, key, [latent, self.context] + ctrl_tensors, body)
             graphs.finish_controller(attn_ctrl, proto, len(ts))
             return [o.clone() for o in outs]
 

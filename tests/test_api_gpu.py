@@ -253,3 +253,63 @@ def test_library_graph_cache_equals_eager(sd15_models):
         outs.append(x_inv.clone())
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[2])
     p2p.register_attention_control(rev, None)
+
+
+def test_edit_controllers_replay_from_the_graph_cache(sd15_models):
+    """BASELINE configs[2] is launch-bound when the edit loop runs eagerly (~350 launches per U-Net forward plus the
+    controller's tensor ops, issued from Python). Fresh AttentionRefine / AttentionReplace / AttentionReweight
+    controllers (with LocalBlend) are captured too: their per-edit tensors are inputs of the graph, so the NEXT edit —
+    another controller object, other prompts — replays it. Results, stored maps and counters must equal the eager
+    run bit for bit."""
+    from invertible_cd_b200 import generation, graphs, p2p
+    from toy_tokenizer import ToyTokenizer
+    cfg, ldm, rev, fwd, _, _ = sd15_models
+    solver = _solver(ldm, rev, fwd)
+    p2p.tokenizer, p2p.device, p2p.NUM_DDIM_STEPS = ToyTokenizer(), "cuda", 4
+    cases = {
+        "refine": [(["a photo of a house on a mountain", "a photo of a house on a mountain at winter evening"],
+                    dict(is_replace_controller=False, blend_words=(("mountain",), ("mountain",)))),
+                   (["a cat sits on a sofa", "a cat sits on a sofa under a lamp"],
+                    dict(is_replace_controller=False, blend_words=(("sofa",), ("sofa",))))],
+        "replace": [(["a photo of a house", "a photo of a castle"], dict(is_replace_controller=True)),
+                    (["a small dog runs fast", "a small cat runs fast"], dict(is_replace_controller=True))],
+        "reweight": [(["a photo of a snowy house", "a photo of a snowy house"],
+                      dict(is_replace_controller=False, equilizer_params={"words": ("snowy",), "values": (3.0,)})),
+                     (["a very tall tree", "a very tall tree"],
+                      dict(is_replace_controller=False, equilizer_params={"words": ("tall",), "values": (0.5,)}))],
+    }
+
+    def run(prompts, kw, seed, use_graphs):
+        prev = graphs.set_enabled(use_graphs)
+        try:
+            g = torch.Generator().manual_seed(seed)
+            ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=g).half().float()
+            x_T = torch.randn(1, 4, 64, 64, generator=g)
+            ctrl = p2p.make_controller(prompts, kw["is_replace_controller"], {"default_": 0.4}, 0.6,
+                                       kw.get("blend_words"), kw.get("equilizer_params"))
+            lat, _ = generation.runner(model=rev, prompt=ctx, controller=ctrl, solver=solver, is_cons_forward=True,
+                                       guidance_scale=19.0, latent=x_T, return_type="latent", tau1=0.8, tau2=0.8,
+                                       w_embed_dim=512)
+            torch.cuda.synchronize()
+            return lat, ctrl
+        finally:
+            graphs.set_enabled(prev)
+
+    graphs.clear(rev.unet)
+    before = dict(graphs.stats)
+    for name, variants in cases.items():
+        for i, (prompts, kw) in enumerate(variants + variants[:1]):      # capture, replay (other prompts), replay
+            lat_g, c_g = run(prompts, kw, 100 + i, True)
+            lat_e, c_e = run(prompts, kw, 100 + i, False)
+            assert torch.equal(lat_g, lat_e), (name, i)
+            assert c_g.cur_step == c_e.cur_step == 4 and c_g.cur_att_layer == c_e.cur_att_layer == 0
+            if c_e.local_blend is not None:
+                assert c_g.local_blend.counter == c_e.local_blend.counter == 4
+            assert set(c_g.attention_store) == set(c_e.attention_store)
+            for k in c_e.attention_store:
+                assert len(c_g.attention_store[k]) == len(c_e.attention_store[k]), (name, k)
+                for a, b in zip(c_g.attention_store[k], c_e.attention_store[k]):
+                    assert torch.equal(a, b), (name, k)
+    assert graphs.stats["captures"] - before["captures"] == 3           # one graph per controller kind
+    assert graphs.stats["replays"] - before["replays"] == 9
+    p2p.register_attention_control(rev, None)
