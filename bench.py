@@ -52,7 +52,7 @@ WORKLOADS = {
 }
 SDXL_CFG3_GLOBAL_BATCH = 32
 FAMILIES = (("gemm", ("gemm_tc_kernel", "gemm2sm_tc_kernel", "splitk_reduce_kernel")),
-            ("attention", ("attention_tc_kernel",)),
+            ("attention", ("attention_tc_kernel", "attention_smallkv_kernel")),
             ("groupnorm", ("gn_fused_kernel", "gn_stats_kernel", "gn_apply_kernel")),
             ("layernorm", ("layernorm_kernel",)))
 
@@ -499,7 +499,7 @@ def measure(wl_key, B, args, rank, world, local_rank, device, full, capture_self
         ops.profile = None
     peak_tf, peak_hbm = peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_c_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(wl_key)

@@ -48,7 +48,7 @@ def main(csv_path, shapes_path, top=40):
     agg = defaultdict(lambda: [0, 0.0, 0.0])
     for name, ns in rows:
         kind = ("gemm_tc" if ("gemm_tc_kernel" in name or "gemm2sm_tc_kernel" in name)
-                else "attention_tc" if "attention_tc_kernel" in name else None)
+                else "attention_tc" if ("attention_tc_kernel" in name or "attention_smallkv_kernel" in name) else None)
         if kind is None:
             continue
         try:
@@ -70,7 +70,7 @@ def main(csv_path, shapes_path, top=40):
     return fam
 
 
-FAMILIES = {"gemm": ("gemm_tc_kernel", "gemm2sm_tc_kernel", "splitk_reduce_kernel"), "attention": ("attention_tc_kernel",),
+FAMILIES = {"gemm": ("gemm_tc_kernel", "gemm2sm_tc_kernel", "splitk_reduce_kernel"), "attention": ("attention_tc_kernel", "attention_smallkv_kernel"),
             "groupnorm": ("gn_fused_kernel", "gn_stats_kernel", "gn_apply_kernel"), "layernorm": ("layernorm_kernel",)}
 
 
