@@ -12,7 +12,12 @@
 
 namespace icd {
 
-constexpr int GN_THREADS = 320;   // multiple of every (C/8) <= 320 that occurs: 40, 80, 160, 320 (120/240 leave idle lanes)
+#ifndef ICD_GN_THREADS
+#define ICD_GN_THREADS 320
+#endif
+constexpr int GN_THREADS = ICD_GN_THREADS;   // multiple of every (C/8) <= 320 that occurs: 40, 80, 160, 320 (120/240 leave idle lanes)
+// dynamic shared memory the single-pass kernel may use: 227 KB per SM minus its static arrays (s_part, s_mean, s_rstd)
+constexpr int GN_FUSED_SMEM_MAX = 220 * 1024 - (GN_THREADS > 320 ? (GN_THREADS - 320) * 16 : 0);
 constexpr int GN_MAX_CHUNKS = 64; // pixel chunks per image -> workspace = B * 64 * 2 * 32 floats
 
 struct GnSrc {
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, int apply_chunks, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
-                const float* __restrict__ ws) {
+                const float* __restrict__ ws, double inv_n) {
   const int C = src.C0 + src.C1;
   const int vpr = C >> 3;
   const int rows_per_iter = GN_THREADS / vpr;
@@ -131,9 +136,18 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
     const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
     double s = 0.0, q = 0.0;
     const float* w = ws + static_cast<long long>(b) * chunks * 64;
-    for (int i = l; i < chunks; i += 8) {
-      s += static_cast<double>(w[i * 64 + g]);
-      q += static_cast<double>(w[i * 64 + 32 + g]);
+    float sv[8], qv[8];                       // all partials requested up front: one L2 round trip (see gn_fused_kernel)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = l + 8 * k;
+      const bool ok = i < chunks;
+      sv[k] = ok ? w[i * 64 + g] : 0.f;
+      qv[k] = ok ? w[i * 64 + 32 + g] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s += static_cast<double>(sv[k]);
+      q += static_cast<double>(qv[k]);
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
@@ -141,12 +155,14 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
       q += __shfl_xor_sync(0xffffffffu, q, o);
     }
     if (l == 0) {
-      const double n = static_cast<double>(HW) * cpg;
-      const double mean = s / n;
-      double var = q / n - mean * mean;
+      // E[x^2] - mean^2 stays in fp64 (cancellation); the reciprocal of the count comes from the host and the
+      // inverse square root runs on the fp32 MUFU: fp64 division and square root are long software sequences that
+      // sat on the critical path of every CTA right behind the grid barrier (tools/gn_prof.py)
+      const double mean = s * inv_n;
+      double var = q * inv_n - mean * mean;
       if (var < 0.0) var = 0.0;
       s_mean[g] = static_cast<float>(mean);
-      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
     }
   }
   __syncthreads();
@@ -204,9 +220,21 @@ gn_apply_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
 // there is nothing to reset between CUDA-graph replays. The host picks this path only when chunks * B fits
 // (occupancy calculator, gn_fused_plan); otherwise the two-kernel path above runs. pdl_wait() precedes every
 // global access.
+#ifdef ICD_GN_PROFILE
+// debug builds only (make VARIANT=gnprof EXTRA_DEFS=-DICD_GN_PROFILE, tools/gn_prof.py): clock64 stamps of thread 0 of
+// the first 256 CTAs of the LAST gn_fused launch: [cta][8] = start | after pdl_wait | loads issued+stored | partials
+// published | grid barrier passed | statistics final | written out
+__device__ long long* g_gn_prof = nullptr;
+#define ICD_GN_STAMP(k)                                                                                   \
+  if (threadIdx.x == 0 && g_gn_prof != nullptr && blockIdx.y * gridDim.x + blockIdx.x < 256)               \
+    g_gn_prof[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = clock64();
+#else
+#define ICD_GN_STAMP(k)
+#endif
+
 __global__ void __launch_bounds__(GN_THREADS)
 gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, float eps,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, float* ws) {
+                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, float* ws, double inv_n) {
   extern __shared__ uint4 s_x[];               // [rows of this chunk][vpr] 16-byte vectors
   __shared__ float4 s_part[GN_THREADS];
   __shared__ float s_mean[32], s_rstd[32];
@@ -222,7 +250,9 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
   const int rows_per_chunk = (HW + chunks - 1) / chunks;
   const int p0 = chunk * rows_per_chunk;
   const int p1 = min(HW, p0 + rows_per_chunk);
+  ICD_GN_STAMP(0)
   pdl_wait();
+  ICD_GN_STAMP(1)
   // ---- pass 1: global -> shared, partial sums (each thread only ever touches its own smem slots)
   float sl = 0.f, ql = 0.f, sh = 0.f, qh = 0.f;
   auto accum = [&](const uint4& raw) {
@@ -241,7 +271,21 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
   };
   if (active) {
     int pix = p0 + r;
-    for (; pix + 3 * rows_per_iter < p1; pix += 4 * rows_per_iter) {   // four independent 16-byte loads in flight
+    // eight independent 16-byte loads in flight per thread: with ONE CTA (320 threads) per SM the read phase is bound
+    // by bytes in flight (Little's law), not by bandwidth; the accumulation order is unchanged (row order)
+    for (; pix + 7 * rows_per_iter < p1; pix += 8 * rows_per_iter) {
+      uint4 raw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        raw[u] = *reinterpret_cast<const uint4*>(
+            gn_vec_ptr(src, static_cast<long long>(b) * HW + pix + u * rows_per_iter, c));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s_x[(pix - p0 + u * rows_per_iter) * vpr + v] = raw[u];
+        accum(raw[u]);
+      }
+    }
+    for (; pix + 3 * rows_per_iter < p1; pix += 4 * rows_per_iter) {
       uint4 raw[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
@@ -261,6 +305,7 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
   }
   s_part[threadIdx.x] = make_float4(sl, ql, sh, qh);
   __syncthreads();
+  ICD_GN_STAMP(2)
   if (threadIdx.x < 32) {
     // same fixed-order gather as gn_stats_kernel (deterministic: no floating-point atomics anywhere)
     const int g = threadIdx.x;
@@ -287,16 +332,30 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
   }
   // ---- publish, then wait until every chunk has published: grid-wide barrier of the cooperative launch
   __threadfence();
+  ICD_GN_STAMP(3)
   cooperative_groups::this_grid().sync();
+  ICD_GN_STAMP(4)
   pdl_launch_dependents();
   // ---- finalize the statistics (every CTA of the image does this redundantly: 8 lanes per group, fp64, fixed order)
   if (threadIdx.x < 256) {
     const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
     double s = 0.0, q = 0.0;
     const float* w = ws + static_cast<long long>(b) * chunks * 64;
-    for (int i = l; i < chunks; i += 8) {
-      s += static_cast<double>(__ldcg(w + i * 64 + g));
-      q += static_cast<double>(__ldcg(w + i * 64 + 32 + g));
+    // all (<= GN_MAX_CHUNKS / 8 = 8 per lane) partials are requested before the first one is consumed: ONE L2 round
+    // trip instead of a chain of them (tools/gn_prof.py: this phase was 7.0k of the kernel's 28.7k cycles); same summation order
+    static_assert(GN_MAX_CHUNKS <= 64, "finalize holds 8 partials per lane");
+    float sv[8], qv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = l + 8 * k;
+      const bool ok = i < chunks;
+      sv[k] = ok ? __ldcg(w + i * 64 + g) : 0.f;
+      qv[k] = ok ? __ldcg(w + i * 64 + 32 + g) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s += static_cast<double>(sv[k]);
+      q += static_cast<double>(qv[k]);
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
@@ -304,15 +363,18 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
       q += __shfl_xor_sync(0xffffffffu, q, o);
     }
     if (l == 0) {
-      const double n = static_cast<double>(HW) * cpg;
-      const double mean = s / n;
-      double var = q / n - mean * mean;
+      // E[x^2] - mean^2 stays in fp64 (cancellation); the reciprocal of the count comes from the host and the
+      // inverse square root runs on the fp32 MUFU: fp64 division and square root are long software sequences that
+      // sat on the critical path of every CTA right behind the grid barrier (tools/gn_prof.py)
+      const double mean = s * inv_n;
+      double var = q * inv_n - mean * mean;
       if (var < 0.0) var = 0.0;
       s_mean[g] = static_cast<float>(mean);
-      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
     }
   }
   __syncthreads();
+  ICD_GN_STAMP(5)
   // (the partials in `ws` are overwritten by the NEXT GroupNorm launch only: stream order / pdl_wait() there)
   if (!active) return;
   // ---- pass 2: shared -> normalise (+SiLU) -> global
@@ -323,7 +385,7 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
     a[j] = s_rstd[g] * gamma[c + j];
     sft[j] = beta[c + j] - s_mean[g] * a[j];
   }
-  for (int pix = p0 + r; pix < p1; pix += rows_per_iter) {
+  auto emit = [&](int pix) {
     const uint4 raw = s_x[(pix - p0) * vpr + v];
     const __half* h = reinterpret_cast<const __half*>(&raw);
     uint4 outv;
@@ -335,7 +397,18 @@ gn_fused_kernel(GnSrc src, __half* __restrict__ y, int HW, int cpg, int chunks, 
       o[j] = __float2half_rn(x);
     }
     *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * HW + pix) * C + c) = outv;
+  };
+  {
+    // four rows per iteration: 32 independent cvt -> fma -> tanh -> fma -> cvt chains cover the MUFU latency that a
+    // single CTA per SM (10 warps) cannot hide by switching warps
+    int pix = p0 + r;
+    for (; pix + 3 * rows_per_iter < p1; pix += 4 * rows_per_iter) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) emit(pix + u * rows_per_iter);
+    }
+    for (; pix < p1; pix += rows_per_iter) emit(pix);
   }
+  ICD_GN_STAMP(6)
 }
 
 // one warp per row; values stay in registers between the mean and variance passes
@@ -439,14 +512,20 @@ static bool gn_fused_plan(int B, int HW, int C, int* chunks_out, size_t* smem_ou
   if (!enabled || B > 1024 || B < 1 || HW < 1) return false;
   static PerDeviceFlag configured;
   if (!configured.cur()) {
-    if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_FUSED_SMEM_MAX) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
     configured.cur() = true;
   }
   const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS);
-  for (int cps = 4; cps >= 1; --cps) {
+  // CTAs per SM to aim for: more, smaller CTAs keep more loads in flight; fewer, fatter ones make the grid barrier and
+  // the (per-CTA, redundant) statistics finalize cheaper. ICD_GN_CPS overrides for the sweep in tools/gn_bench.py.
+  // Measured (profiles/r2_c_gn_cps_sweep.txt): ONE CTA per SM wins on every shape of both networks (8x64^2x320:
+  // 20.0 -> 13.7 us, 8x32^2x640: 16.9 -> 10.2 us) — at 4 per SM the barrier took 7.3k and the finalize 7.1k cycles of a
+  // 29.8k-cycle kernel (512 CTAs each re-reading all partials of their image from L2), at 1 per SM 3.0k and 1.7k.
+  static const int cps_max = [] { const char* e = getenv("ICD_GN_CPS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+  for (int cps = cps_max; cps >= 1; --cps) {
     int fc = (sm_count() * cps) / B;
     if (fc > GN_MAX_CHUNKS) fc = GN_MAX_CHUNKS;
     if (fc > max_by_rows) fc = max_by_rows;
@@ -454,7 +533,7 @@ static bool gn_fused_plan(int B, int HW, int C, int* chunks_out, size_t* smem_ou
     if (fc < 1) continue;
     const int rows = (HW + fc - 1) / fc;
     const size_t smem = static_cast<size_t>(rows) * C * 2;
-    if (smem > 220 * 1024) continue;
+    if (smem > static_cast<size_t>(GN_FUSED_SMEM_MAX)) continue;
     int granted = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&granted, gn_fused_kernel, GN_THREADS, smem) != cudaSuccess) {
       cudaGetLastError();
@@ -467,6 +546,17 @@ static bool gn_fused_plan(int B, int HW, int C, int* chunks_out, size_t* smem_ou
   }
   return false;
 }
+
+#ifdef ICD_GN_PROFILE
+extern "C" long long* icd_gn_prof_buffer(void) {
+  static long long* buf = nullptr;
+  if (buf == nullptr) {
+    cudaMallocManaged(&buf, 256 * 8 * sizeof(long long));
+    cudaMemcpyToSymbol(g_gn_prof, &buf, sizeof(buf));
+  }
+  return buf;
+}
+#endif
 
 extern "C" int icd_groupnorm_launches(int B, int HW, int C) {
   int fc = 0;
@@ -487,12 +577,13 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   GnSrc src{reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), C0, x1 != nullptr ? C1 : 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_by_rows = (HW * (C / 8) + 4 * GN_THREADS - 1) / (4 * GN_THREADS);
+  const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
   // ---- single-pass path: every CTA of an image must be resident at once (see gn_fused_kernel)
   int fc = 0;
   size_t fsmem = 0;
   if (gn_fused_plan(B, HW, C, &fc, &fsmem)) {
     const cudaError_t e = launch_k_coop(gn_fused_kernel, dim3(fc, B), dim3(GN_THREADS), fsmem, st, src,
-                                        reinterpret_cast<__half*>(y), HW, cpg, fc, eps, gamma, beta, apply_silu, stats_ws);
+                                        reinterpret_cast<__half*>(y), HW, cpg, fc, eps, gamma, beta, apply_silu, stats_ws, inv_n);
     if (e == cudaSuccess) return check_launch("gn_fused");
     if (e != cudaErrorCooperativeLaunchTooLarge) return set_error(std::string("gn_fused launch: ") + cudaGetErrorString(e));
     cudaGetLastError();   // the driver could not co-schedule the grid (e.g. a partitioned device): two-kernel path
@@ -510,7 +601,7 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   if (apply_chunks > HW) apply_chunks = HW;
   if (apply_chunks < 1) apply_chunks = 1;
   launch_k(gn_apply_kernel, dim3(apply_chunks, B), dim3(GN_THREADS), 0, st, src, reinterpret_cast<__half*>(y), HW, cpg, chunks,
-                                                                apply_chunks, eps, gamma, beta, apply_silu, stats_ws);
+                                                                apply_chunks, eps, gamma, beta, apply_silu, stats_ws, inv_n);
   return check_launch("gn_apply");
 }
 
