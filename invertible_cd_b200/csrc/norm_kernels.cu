@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/icd_b200.h"
 #include "host_util.h"
@@ -590,13 +591,21 @@ extern "C" int icd_groupnorm(const void* x0, int C0, const void* x1, int C1, voi
   }
   // stats chunks index the caller's workspace ([B][chunks][2][32] floats, contract: B * 4096 floats): never more
   // than GN_MAX_CHUNKS per image
-  int chunks = (4 * sm_count() + B - 1) / B;
+  // CTAs per SM of the two-kernel path (ICD_GN2_CPS = "stats,apply"; sweep in profiles/r2_c_gn_cps_sweep.txt)
+  static const int cps_stats = [] { const char* e = getenv("ICD_GN2_CPS"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  static const int cps_apply = [] {
+    const char* e = getenv("ICD_GN2_CPS");
+    const char* c = e ? strchr(e, ',') : nullptr;
+    const int v = c ? atoi(c + 1) : 4;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  int chunks = (cps_stats * sm_count() + B - 1) / B;
   if (chunks > max_by_rows) chunks = max_by_rows;
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
   if (chunks < 1) chunks = 1;
   launch_k(gn_stats_kernel, dim3(chunks, B), dim3(GN_THREADS), 0, st, src, HW, cpg, chunks, stats_ws);
   if (check_launch("gn_stats")) return 1;
-  int apply_chunks = (4 * sm_count() + B - 1) / B;
+  int apply_chunks = (cps_apply * sm_count() + B - 1) / B;
   if (apply_chunks > max_by_rows) apply_chunks = max_by_rows;
   if (apply_chunks > HW) apply_chunks = HW;
   if (apply_chunks < 1) apply_chunks = 1;
