@@ -142,6 +142,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   static_assert((1 + 3 * ST + 7 * MT) * 8 + 4 <= 384, "barrier block overflows into the ones tile");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ICD_ATTN_PROFILE
+  const long long cta_t0 = clock64();   // CTA timeline (slots 16..): set-up | Q landed | first S | key loop | epilogue
+#define ICD_CTA_STAMP(k) if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && warp == 1 + MT && lane == 0) p.prof[16 + (k)] = clock64() - cta_t0;
+#else
+#define ICD_CTA_STAMP(k)
+#endif
   const int q_tiles = (p.Nq + 128 * MT - 1) / (128 * MT);
   const int qt = blockIdx.x % q_tiles;
   const int bh = blockIdx.x / q_tiles;
@@ -177,6 +183,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  ICD_CTA_STAMP(0)
   pdl_wait();   // prologue above overlaps the previous kernel's tail; Q/K/V are read below
   // per query tile m (column offset m * TILE_COLS): S0 | S1 | O | L | Q
   constexpr uint32_t OFF_O = 128, OFF_L = 128 + DP, OFF_Q = 128 + DP + 16;
@@ -296,6 +303,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // move this thread's Q row from the 128B-swizzled smem tile into tensor memory (A operand of S = Q.K^T);
     // rows beyond N_q were zero-filled by TMA
     mbar_wait(q_full, 0);
+    ICD_CTA_STAMP(1)
 #pragma unroll
     for (int a = 0; a < DATOMS; ++a) {
       uint32_t qr[32];
@@ -317,6 +325,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       ICD_PROF_MARK(6)
       mbar_wait(&s_full_m[bsel], (j >> 1) & 1);
       tc_fence_after();
+      if (j == 0) { ICD_CTA_STAMP(2) }
       ICD_PROF_MARK(0)
       const int valid = min(BKV, p.Nk - j * BKV);
       float s[64];
@@ -441,6 +450,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && quad == 0 && lane == 0)
       for (int k = 0; k < 7; ++k) p.prof[m * 8 + k] = pt_[k];
 #endif
+    ICD_CTA_STAMP(3)
     // epilogue: O / l -> fp16 -> global   (l = row sum accumulated by the ones-MMA)
     mbar_wait(&pv_done_m[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
@@ -543,6 +553,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   }
+  ICD_CTA_STAMP(4)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -582,6 +593,9 @@ extern "C" void icd_attention_prof_dump(int n_kv) {
     for (int k = 0; k < 7; ++k) printf("  %s %.0f", names[k], double(g_prof_buf_last[m * 8 + k]) / n_kv);
     printf("\n");
   }
+  const long long* c = g_prof_buf_last + 16;
+  printf("  CTA timeline (cycles since CTA start, softmax warp 0 of tile 0): set-up done %lld | Q landed %lld | first S %lld | "
+         "key loop done %lld | epilogue done %lld\n", c[0], c[1], c[2], c[3], c[4]);
 }
 #endif
 
@@ -633,10 +647,10 @@ extern "C" int icd_attention_ex(const void* q, const void* k, const void* v, voi
   p.speculate = spec_env;
 #ifdef ICD_ATTN_PROFILE
   static long long* prof_buf = nullptr;
-  if (prof_buf == nullptr) cudaMallocManaged(&prof_buf, 16 * sizeof(long long));
+  if (prof_buf == nullptr) cudaMallocManaged(&prof_buf, 32 * sizeof(long long));
   p.prof = prof_buf;
   g_prof_buf_last = prof_buf;
-  for (int i = 0; i < 16; ++i) prof_buf[i] = 0;
+  for (int i = 0; i < 32; ++i) prof_buf[i] = 0;
 #endif
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // Tuning knobs, fixed per head dim from the sweeps in profiles/README.md (r1h; r2_c with the speculative softmax,

@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from invertible_cd_b200 import _lib, ops  # noqa: E402
 
-for (B, H, Nq, Nk, D) in [(8, 8, 4096, 4096, 40), (4, 10, 4096, 4096, 64)]:
+for (B, H, Nq, Nk, D) in [(8, 8, 4096, 4096, 40), (4, 10, 4096, 4096, 64), (4, 20, 1024, 1024, 64), (8, 8, 1024, 1024, 80)]:
     q = torch.randn(B * Nq, H * D, device="cuda").half()
     k = torch.randn(B * Nk, H * D, device="cuda").half()
     v = torch.randn(B * Nk, H * D, device="cuda").half()
