@@ -525,8 +525,10 @@ static bool gn_fused_plan(int B, int HW, int C, int* chunks_out, size_t* smem_ou
   // Measured (profiles/r2_c_gn_cps_sweep.txt): ONE CTA per SM wins on every shape of both networks (8x64^2x320:
   // 20.0 -> 13.7 us, 8x32^2x640: 16.9 -> 10.2 us) — at 4 per SM the barrier took 7.3k and the finalize 7.1k cycles of a
   // 29.8k-cycle kernel (512 CTAs each re-reading all partials of their image from L2), at 1 per SM 3.0k and 1.7k.
-  static const int cps_max = [] { const char* e = getenv("ICD_GN_CPS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
-  for (int cps = cps_max; cps >= 1; --cps) {
+  // Denser plans are tried only when the sparser one does not exist (more images than SMs, or a chunk too large for
+  // one CTA's shared memory).
+  static const int cps_first = [] { const char* e = getenv("ICD_GN_CPS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+  for (int cps = cps_first; cps <= 4; ++cps) {
     int fc = (sm_count() * cps) / B;
     if (fc > GN_MAX_CHUNKS) fc = GN_MAX_CHUNKS;
     if (fc > max_by_rows) fc = max_by_rows;

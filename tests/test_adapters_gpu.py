@@ -108,3 +108,32 @@ def test_adapter_errors(models):
     with pytest.raises(KeyError):
         shared.add_adapter("bad", {"unet.base_model.model.not_a_module.lora_A.weight": torch.zeros(8, 4),
                                    "unet.base_model.model.not_a_module.lora_B.weight": torch.zeros(4, 8)})
+
+
+def test_swap_mode_in_fp32():
+    """adapters='swap' with dtype='fp32': the fuse runs on the fp32 GEMM; weights equal the host fuse IN FP32 (base
+    weights held in fp32, as the reference's fp32 pipeline holds them) to fp32 rounding, and a forward through the view
+    equals that resident fp32 model to 1e-5."""
+    from invertible_cd_b200 import arch, loading
+    from invertible_cd_b200.unet import B200UNet
+    cfg = arch.small_sd15_config(time_cond_proj_dim=512)
+    base = {k: v.float() for k, v in arch.synthetic_state_dict(cfg, seed=0).items()}
+    lr = arch.synthetic_lora(cfg, r=8, seed=1, std=0.05)
+    resident = B200UNet(cfg, loading.fuse_lora(base, lr, r=8), "cuda", precision="fp32")
+    s_ldm, s_rev, s_fwd = loading.load_models("synthetic:small_sd15:0", "cuda", lr, None, r=8, w_embed_dim=512,
+                                              dtype="fp32", adapters="swap")
+    assert s_fwd is None and s_rev.unet.precision == "fp32"
+    s_rev.unet.activate()
+    torch.cuda.synchronize()
+    got, ref = _packed_tensors(s_ldm.unet._shared), _packed_tensors(resident)
+    for mod in ref:
+        torch.testing.assert_close(got[mod], ref[mod], rtol=1e-5, atol=1e-7)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 64, 64, generator=g).cuda()
+    ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=g).cuda()
+    wemb = resident.guidance_embedding(resident.cached_vector([3.0, 3.0]), 512)
+    a = resident(x, 500, encoder_hidden_states=ctx, timestep_cond=wemb)["sample"]
+    b = s_rev.unet(x, 500, encoder_hidden_states=ctx, timestep_cond=wemb)["sample"]
+    torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)
+    c = s_ldm.unet(x, 500, encoder_hidden_states=ctx, timestep_cond=wemb)["sample"]     # back to the base weights
+    assert s_ldm.unet._shared.active_adapter is None and not torch.equal(c, b)
