@@ -432,6 +432,45 @@ def init_latent(latent, model, height, width, generator, batch_size):
     return latent, latents
 
 
+def _image_grid(images, num_rows=1, offset_ratio=0.02):
+    """uint8 grid of equally sized (H, W, 3) images, `num_rows` rows, white gutters of `offset_ratio * H` pixels; the
+    image count is padded with white tiles up to `len % num_rows` extra ones, as utils/generation.py:569-591 does."""
+    if isinstance(images, list):
+        tiles = list(images)
+    elif images.ndim == 4:
+        tiles = [img for img in images]
+    else:
+        tiles = [images]
+    extra = 0 if (not isinstance(images, list) and images.ndim != 4) else len(tiles) % num_rows
+    tiles = [np.asarray(t).astype(np.uint8) for t in tiles]
+    tiles += [np.full(tiles[0].shape, 255, dtype=np.uint8)] * extra
+    h, w, _ = tiles[0].shape
+    gap = int(h * offset_ratio)
+    num_cols = len(tiles) // num_rows
+    grid = np.full((h * num_rows + gap * (num_rows - 1), w * num_cols + gap * (num_cols - 1), 3), 255, dtype=np.uint8)
+    for idx in range(num_rows * num_cols):
+        i, j = divmod(idx, num_cols)
+        grid[i * (h + gap):i * (h + gap) + h, j * (w + gap):j * (w + gap) + w] = tiles[idx]
+    return grid
+
+
+def to_pil_images(images, num_rows=1, offset_ratio=0.02):
+    """Image grid as a PIL image (utils/generation.py:569-593; called by running/sd1.5/edit.py:457-458)."""
+    from PIL import Image
+    return Image.fromarray(_image_grid(images, num_rows, offset_ratio))
+
+
+def view_images(images, num_rows=1, offset_ratio=0.02):
+    """Notebook helper of utils/generation.py:596-620: shows the grid with IPython's `display` when there is one."""
+    img = to_pil_images(images, num_rows, offset_ratio)
+    try:
+        from IPython.display import display
+        display(img)
+    except ImportError:
+        pass
+    return img
+
+
 def load_512(image_path, left=0, right=0, top=0, bottom=0):
     """RGB -> plain resize to 512x512 uint8; the crop offsets are accepted and ignored (App. C-5, :546-566)."""
     from PIL import Image

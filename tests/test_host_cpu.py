@@ -567,3 +567,39 @@ def test_adapter_factors_land_in_the_packed_layout():
         ulp = torch.clamp(want.abs(), min=6.1e-5) * 2.0 ** -10
         assert ((got - want).abs() / ulp).max().item() <= 1.01, mod
         assert not torch.equal(want, base.half().float()), mod
+
+
+def test_image_grid_helpers_match_the_reference():
+    """generation.to_pil_images (called by running/sd1.5/edit.py:457-458): same pixels as the reference's helper for a
+    single image, a batch array, a list, and a ragged count that needs white padding tiles."""
+    import numpy as np
+    from invertible_cd_b200 import generation
+    ref_path = "/root/reference/utils/generation.py"
+    rng = np.random.default_rng(0)
+    batch = rng.integers(0, 256, size=(5, 16, 12, 3)).astype(np.float32)
+    cases = [(batch[0], 1), (batch[:4], 2), ([b for b in batch[:4]], 1), (batch[:3], 2), ([b for b in batch], 2),
+             (batch[:1], 2)]
+    if os.path.exists(ref_path):
+        import importlib.util
+        import types
+        stubs = {}
+        for name in ("diffusers", "cv2", "IPython", "IPython.display"):
+            if name not in sys.modules:
+                stubs[name] = sys.modules[name] = types.ModuleType(name)
+        sys.modules["IPython.display"].display = lambda *a, **k: None
+        try:
+            src = open(ref_path).read()
+            start, end = src.index("def to_pil_images"), src.index("def view_images")
+            ns = {"np": np}
+            from PIL import Image
+            ns["Image"] = Image
+            exec(compile(src[start:end], ref_path, "exec"), ns)
+            for imgs, rows in cases:
+                want = np.asarray(ns["to_pil_images"](imgs, rows))
+                got = np.asarray(generation.to_pil_images(imgs, rows))
+                assert got.shape == want.shape and (got == want).all(), (rows, got.shape, want.shape)
+        finally:
+            for name in stubs:
+                sys.modules.pop(name, None)
+    g = np.asarray(generation.to_pil_images(batch[:4], 2))
+    assert g.shape == (2 * 16 + 0, 2 * 12 + 0, 3) and (g[:16, :12] == batch[0].astype(np.uint8)).all()
