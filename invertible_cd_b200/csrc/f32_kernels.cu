@@ -5,7 +5,7 @@
 // every activation is fp32 and the contractions run on the FMA pipe with fp32 accumulation — no tensor-core operand
 // rounding, no fp16 activation storage. It exists so that the hot path can be checked element-wise against the fp32
 // CPU oracle (rtol 1e-3 / atol 1e-4 holds with two orders of magnitude to spare) and so that `dtype='fp32'` means
-// what it means in the reference. It is a correctness mode: ~20x slower than the fp16 path, not benchmarked.
+// what it means in the reference. It is a correctness mode (SGEMM 15-25 TFLOP/s; one SD1.5 row-forward 111 ms vs 8.8 ms in fp16, tools/f32_speed.py).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(256) sgemm_f32_kernel(const IcdSgemm p) {
     return bm[static_cast<long long>(n) * p.b_ld + k];
   };
 
-  for (int k0 = 0; k0 < K; k0 += SG_BK) {
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  // operands of one K block -> registers (the block after the one being multiplied: its latency hides under the FMAs)
+  auto fetch = [&](int k0, float4& av, float4& bv) {
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
     {
       const int k = k0 + a_kq;
       if (vec && am < p.M && k + 3 < K) {
@@ -123,6 +125,10 @@ __global__ void __launch_bounds__(256) sgemm_f32_kernel(const IcdSgemm p) {
         bv = make_float4(load_b_elem(n, k), load_b_elem(n, k + 1), load_b_elem(n, k + 2), load_b_elem(n, k + 3));
       }
     }
+  };
+  float4 av, bv;
+  fetch(0, av, bv);
+  for (int k0 = 0; k0 < K; k0 += SG_BK) {
     __syncthreads();   // previous tile consumed
     As[a_kq + 0][a_row] = av.x;
     As[a_kq + 1][a_row] = av.y;
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(256) sgemm_f32_kernel(const IcdSgemm p) {
       Bs[b_q + 3][b_row] = bv.w;
     }
     __syncthreads();
+    if (k0 + SG_BK < K) fetch(k0 + SG_BK, av, bv);
 #pragma unroll
     for (int kk = 0; kk < SG_BK; ++kk) {
       const float4 a_lo = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
