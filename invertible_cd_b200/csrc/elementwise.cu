@@ -125,8 +125,7 @@ __global__ void __launch_bounds__(256) act_kernel(const __half2* __restrict__ x,
     } else if (kind == 1) {
       r = make_float2(v.x / (1.0f + expf(-1.702f * v.x)), v.y / (1.0f + expf(-1.702f * v.y)));
     } else {
-      r = make_float2(0.5f * v.x * (1.0f + erff(v.x * 0.70710678118654752f)),
-                      0.5f * v.y * (1.0f + erff(v.y * 0.70710678118654752f)));
+      r = make_float2(gelu_erf(v.x), gelu_erf(v.y));
     }
     y[i] = __floats2half2_rn(r.x, r.y);
   }
