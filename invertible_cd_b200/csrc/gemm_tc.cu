@@ -464,10 +464,14 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
                        gemm2sm_wanted(g->M, g->N, g->K0, g->geglu != 0);
   const bool warp_epi = warp_epi_enabled && p.epi_tma && !g->geglu && !use_2sm &&
                         (g->residual == nullptr || g->alpha == 1.0f);   // the MMA-added residual is not scaled by alpha
+  // GEGLU projections that stay on the single-CTA kernel (K < 1024): per-warp epilogue too (ICD_GEMM_WARP_GEGLU=0:
+  // the CTA-wide staged one)
+  static const bool warp_geglu_enabled = [] { const char* e = getenv("ICD_GEMM_WARP_GEGLU"); return e == nullptr || atoi(e) != 0; }();
+  const bool warp_geglu = warp_epi_enabled && warp_geglu_enabled && p.epi_tma && g->geglu && !use_2sm;
   if (p.epi_tma) {
     const uint64_t n_out = (uint64_t)(g->geglu ? g->N / 2 : g->N);
     const uint64_t z2 = (uint64_t)((g->Z + p.ZA1 - 1) / p.ZA1);
-    const uint32_t box[4] = {32, warp_epi ? 32u : 128u, 1, 1};
+    const uint32_t box[4] = {32, (warp_epi || warp_geglu) ? 32u : 128u, 1, 1};
     const uint64_t dims[4] = {n_out, (uint64_t)g->M, (uint64_t)p.ZA1, z2};
     const uint64_t s1 = g->out_z1_stride > 0 ? (uint64_t)g->out_z1_stride * 2 : (uint64_t)g->ldc * 2;
     const uint64_t s2 = g->out_z2_stride > 0 ? (uint64_t)g->out_z2_stride * 2 : s1;
@@ -513,6 +517,10 @@ extern "C" int icd_gemm(const IcdGemm* g, void* stream) {
   }
   if (g->geglu) {
     if (bm != 128) return set_error("icd_gemm: GEGLU uses 128-row tiles");
+    if (warp_geglu) {
+      if (bn == 128) ICD_LAUNCH(128, 128, EPI_WARP_GEGLU);
+      if (bn == 256) ICD_LAUNCH(128, 256, EPI_WARP_GEGLU);
+    }
     if (bn == 128) ICD_LAUNCH(128, 128, EPI_STAGED_GEGLU);
     if (bn == 256) ICD_LAUNCH(128, 256, EPI_STAGED_GEGLU);
     return set_error("icd_gemm: GEGLU supports BN 128 / 256");

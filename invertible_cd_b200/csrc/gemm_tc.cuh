@@ -88,7 +88,7 @@ struct GemmParams {
 #endif
 
 enum : int { EPI_DIRECT = 0, EPI_STAGED = 1, EPI_STAGED_GEGLU = 2, EPI_STAGED_RES = 3, EPI_STAGED_F32 = 4,
-             EPI_WARP = 5 };
+             EPI_WARP = 5, EPI_WARP_GEGLU = 6 };
 
 template <int BM_, int BN, int EPI>
 struct GemmCfg {
@@ -563,6 +563,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       if (lane0) bulk_wait0();
       if (warp == 2 && lane0) ICD_GSTAMP(6);
+    } else if constexpr (EPI == EPI_WARP_GEGLU) {
+      // ---- per-warp GEGLU epilogue: as EPI_WARP (no CTA-wide barrier, every warp stages and TMA-stores its own
+      // [32 rows x 32 output columns] blocks), with  out = (h * alpha + b_h) * gelu(g * alpha + b_g)  from the hidden
+      // and gate halves of the interleaved accumulator tile (columns [0, BN/2) | [BN/2, BN), packing.pack_geglu).
+      constexpr int outw = BN / 2;
+      constexpr int units = (outw + 63) / 64;
+      const int n_out_total = p.N / 2;
+      const int ew = warp - 2;                       // 0..7
+      uint8_t* my_out = smem_c + ew * 4096;          // 2 x [32 rows x 64 B]
+      const bool lane0 = lane == 0;
+      const uint32_t sw = (lane >> 1) & 3;           // 64B swizzle: 16B-chunk index ^= (row / 2) % 4
+      const int col_w = part * 32;
+      const bool has_bias = p.bias != nullptr;
+      uint32_t ocount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int tz = tile % tiles_all_z;
+        const int z = tz / tiles_per_z;
+        const int t = tz - z * tiles_per_z;
+        const int mt = t / n_tiles, nt = t - mt * n_tiles;
+        const int acc = iter % ACC_STAGES;
+        const uint32_t acc_phase = (iter / ACC_STAGES) & 1;
+        const int n_out0 = nt * outw;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int half = 0; half < HALVES; ++half) {
+          const int row0 = mt * BM + half * 128 + quad * 32;
+          const uint32_t t_half =
+              tmem_base + acc * Cfg::ACC_COLS + half * Cfg::HALF_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+          for (int u = 0; u < units; ++u) {
+            const int col_t = u * 64 + col_w;
+            const int ncol = n_out0 + col_t;
+            if (col_t >= outw || ncol >= n_out_total) continue;   // warp-uniform
+            if (lane0) bulk_wait_read1();
+            __syncwarp();
+            float hv[32], gv[32];
+            tmem_ld32(t_half + col_t, hv);
+            tmem_ld32(t_half + BN / 2 + col_t, gv);
+            tmem_ld_wait();
+            const float4* bh = reinterpret_cast<const float4*>(p.bias + nt * BN + col_t);
+            const float4* bg = reinterpret_cast<const float4*>(p.bias + nt * BN + BN / 2 + col_t);
+            const uint32_t obuf = smem_u32(my_out) + (ocount & 1) * 2048 + lane * 64;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t o[4];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int j4 = cc * 2 + q;
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (has_bias) { b0 = __ldg(bh + j4); b1 = __ldg(bg + j4); }
+                const float r0 = (hv[j4 * 4 + 0] * p.alpha + b0.x) * gelu_erf(gv[j4 * 4 + 0] * p.alpha + b1.x);
+                const float r1 = (hv[j4 * 4 + 1] * p.alpha + b0.y) * gelu_erf(gv[j4 * 4 + 1] * p.alpha + b1.y);
+                const float r2 = (hv[j4 * 4 + 2] * p.alpha + b0.z) * gelu_erf(gv[j4 * 4 + 2] * p.alpha + b1.z);
+                const float r3 = (hv[j4 * 4 + 3] * p.alpha + b0.w) * gelu_erf(gv[j4 * 4 + 3] * p.alpha + b1.w);
+                const __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
+                o[q * 2] = *reinterpret_cast<const uint32_t*>(&h01);
+                o[q * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obuf + ((cc ^ sw) << 4)), "r"(o[0]),
+                           "r"(o[1]), "r"(o[2]), "r"(o[3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane0) {
+              tma_store_4d(&tmOut, my_out + (ocount & 1) * 2048, ncol, row0, z % p.ZA1, z / p.ZA1);
+              bulk_commit();
+            }
+            ++ocount;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+      }
+      if (lane0) bulk_wait0();
     } else if constexpr (EPI != EPI_DIRECT) {
       // ---- staged epilogue: TMEM -> regs -> (+bias/rowvec/residual | GEGLU) -> swizzled smem -> TMA store.
       // Output is produced in 64-column units through a double-buffered staging area (2 x [128 rows x 64 cols],
