@@ -49,10 +49,12 @@ struct SmallKvCfg {
   static constexpr int Q_TILE_BYTES = DATOMS * 16384;  // 128 rows x 128 B per 64-wide atom
   static constexpr int KV_BYTES = DATOMS * KW * 128;   // 80 rows x 128 B per atom
   static constexpr int Q_STAGES = DATOMS == 1 ? 3 : 2;
-  static constexpr int SMEM_BYTES = Q_STAGES * Q_TILE_BYTES + 2 * KV_BYTES + 256;
+  // + 256: barriers and the TMEM pointer; + 1024: slack for the 1024-byte alignment of the dynamic segment when
+  // something (a tool, a future static array) puts static shared memory in front of it
+  static constexpr int SMEM_BYTES = Q_STAGES * Q_TILE_BYTES + 2 * KV_BYTES + 256 + 1024;
   static constexpr int THREADS = 192;
-  static constexpr int MIN_CTAS = (3 * (SMEM_BYTES + 1024) <= 227 * 1024 && 3 * TMEM_COLS <= 512)   ? 3
-                                  : (2 * (SMEM_BYTES + 1024) <= 227 * 1024 && 2 * TMEM_COLS <= 512) ? 2
+  static constexpr int MIN_CTAS = (3 * (SMEM_BYTES + 1024) <= 228 * 1024 && 3 * TMEM_COLS <= 512)   ? 3
+                                  : (2 * (SMEM_BYTES + 1024) <= 228 * 1024 && 2 * TMEM_COLS <= 512) ? 2
                                                                                                      : 1;
 };
 

@@ -3,6 +3,8 @@ op on identical fp16 inputs. Tolerances (stated per test): outputs are fp16, acc
 rtol=1e-3 plus an absolute term of ~1 fp16 ulp of the output scale (atol given per case)."""
 import math
 
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -264,6 +266,8 @@ def test_groupnorm(ops, B, HW, C0, C1, silu):
     y2 = ops.groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=x1)
     y3 = ops.groupnorm(x0, B, HW, gamma, beta, eps, silu, ws, x1=x1)
     assert torch.equal(y, y2) and torch.equal(y, y3)
+    if os.environ.get("PYTORCH_NO_CUDA_MEMORY_CACHING"):
+        return      # compute-sanitizer runs (tools/gpu_sanitizer.sh): no allocation is possible inside a capture
     out = torch.empty_like(y)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
