@@ -18,3 +18,5 @@ for T in tests/test_unet_gpu.py tests/test_adapters_gpu.py tests/test_vae_gpu.py
   timeout 1500 $S --tool memcheck --error-exitcode 9 python -m pytest $T -q -p no:cacheprovider -k "not graph" > gpurun_out/san_memcheck_$N.log 2>&1
   echo "$N rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/san_memcheck_$N.log | tail -2; grep -c "Invalid __" gpurun_out/san_memcheck_$N.log
 done
+timeout 2400 $S --tool memcheck --error-exitcode 9 python -m pytest tests/test_fullsize_gpu.py -q -p no:cacheprovider -k "cfg0 or sdxl_full_row_forward or cfg1" > gpurun_out/san_memcheck_fullsize.log 2>&1
+echo "fullsize rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/san_memcheck_fullsize.log | tail -2; grep -c "Invalid __" gpurun_out/san_memcheck_fullsize.log
