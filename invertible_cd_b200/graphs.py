@@ -57,11 +57,14 @@ _EDIT_TENSORS = ("cross_replace_alpha", "mapper", "alphas", "equalizer")
 _BLEND_TENSORS = ("alpha_layers", "substruct_layers")
 
 
+_REQUIRE_CUDA = True      # CPU tests of the plumbing below switch this off
+
+
 def _tensor_slots(obj, names, tag, sig, slots):
     for a in names:
         t = getattr(obj, a, None)
         if torch.is_tensor(t):
-            if not t.is_cuda:
+            if _REQUIRE_CUDA and not t.is_cuda:
                 return False
             sig.append((tag, a, tuple(t.shape), str(t.dtype)))
             slots.append((tag, a))

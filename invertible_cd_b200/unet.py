@@ -41,6 +41,10 @@ def _f32(t, dev):
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 class B200UNet:
     """Packed weights + forward of one U-Net (teacher, forward-consistency or reverse-consistency model)."""
 
@@ -262,7 +266,7 @@ class B200UNet:
             return
         if name is not None and name not in self._adapters:
             raise KeyError(f"no adapter '{name}' (have {sorted(self._adapters)})")
-        if torch.cuda.is_current_stream_capturing():
+        if _capturing():
             raise RuntimeError("set_adapter inside a CUDA-graph capture: activate the adapter before capturing")
         new = self._adapters[name] if name is not None else {}
         old = self._adapters[self._active] if self._active is not None else {}
@@ -512,7 +516,7 @@ class AdapterView:
 
     def forward(self, *args, **kwargs):
         shared = self._shared
-        if not torch.cuda.is_current_stream_capturing():
+        if not _capturing():
             self.activate()
         elif shared.active_adapter != self._name:
             raise RuntimeError("AdapterView called inside a CUDA-graph capture with another adapter active")

@@ -603,3 +603,100 @@ def test_image_grid_helpers_match_the_reference():
                 sys.modules.pop(name, None)
     g = np.asarray(generation.to_pil_images(batch[:4], 2))
     assert g.shape == (2 * 16 + 0, 2 * 12 + 0, 3) and (g[:16, :12] == batch[0].astype(np.uint8)).all()
+
+
+def test_edit_controller_graph_plumbing(monkeypatch):
+    """graphs.py host logic for the edit controllers (the capture itself is a GPU test): a fresh AttentionRefine /
+    AttentionReplace / AttentionReweight controller yields a hashable signature that depends on its control-flow
+    values but not on its tensor VALUES, lists its per-edit tensors in a fixed order, and the proto controller is a
+    private copy wired to the static tensors; a used controller is not graphable."""
+    import torch
+    from invertible_cd_b200 import graphs, p2p
+    from toy_tokenizer import ToyTokenizer
+    monkeypatch.setattr(graphs, "_REQUIRE_CUDA", False)
+    p2p.tokenizer, p2p.device, p2p.NUM_DDIM_STEPS = ToyTokenizer(), "cpu", 4
+
+    def make(prompts, replace=False, blend=None, eq=None, cross=0.4, self_=0.6):
+        c = p2p.make_controller(prompts, replace, {"default_": cross}, self_, blend, eq)
+        c.num_att_layers = 32
+        return c
+
+    a = make(["a photo of a house on a mountain", "a photo of a house on a mountain at winter evening"],
+             blend=(("mountain",), ("mountain",)))
+    b = make(["a cat sits on a sofa", "a cat sits on a sofa under a lamp"], blend=(("sofa",), ("sofa",)))
+    sig_a, sig_b = graphs.controller_signature(a), graphs.controller_signature(b)
+    assert sig_a is not None and sig_a == sig_b and hash(sig_a) == hash(sig_b)      # other prompts: same graph
+    assert not torch.equal(a.mapper, b.mapper)
+    assert graphs.controller_signature(make(["a photo of a house", "a photo of a castle"], replace=True)) != sig_a
+    assert graphs.controller_signature(make(["a photo of a house on a mountain", "a photo of a house on a mountain at winter evening"],
+                                            blend=(("mountain",), ("mountain",)), self_=0.3)) != sig_a   # other replace window
+    tens = graphs.controller_tensors(a)
+    names = [t.shape for t in tens]
+    assert len(tens) == 4 and tens[0] is a.cross_replace_alpha and tens[1] is a.mapper and tens[2] is a.alphas \
+        and tens[3] is a.local_blend.alpha_layers, names
+    static = [t.clone() for t in tens]
+    proto = graphs.proto_controller(a, static)
+    assert proto is not a and proto.local_blend is not a.local_blend and type(proto) is type(a)
+    assert proto.mapper is static[1] and proto.local_blend.alpha_layers is static[3] and a.mapper is tens[1]
+    assert proto.attention_store == {} and proto.cur_step == 0
+    rw = make(["a photo of a snowy house", "a photo of a snowy house"], eq={"words": ("snowy",), "values": (3.0,)})
+    t_rw = graphs.controller_tensors(rw)
+    assert any(t is rw.equalizer for t in t_rw) and any(t is rw.prev_controller.mapper for t in t_rw)
+    p_rw = graphs.proto_controller(rw, [t.clone() for t in t_rw])
+    assert p_rw.prev_controller is not rw.prev_controller
+    graphs.finish_controller(a, proto, 4)
+    assert a.cur_step == 4 and a.local_blend.counter == 4
+    assert graphs.controller_signature(a) is None and graphs.controller_tensors(a) == []     # used: eager from now on
+    assert graphs.controller_signature(p2p.AttentionStore()) is not None and graphs.controller_signature(None) == ("none",)
+
+
+def test_adapter_view_forwards_and_isolates():
+    """unet.AdapterView without a GPU: attribute reads go to the shared executor, `controller` and the graph cache are
+    per view, every call activates the view's adapter first and runs the shared executor with the view's controller."""
+    from invertible_cd_b200 import graphs
+    from invertible_cd_b200.unet import AdapterView
+
+    class Shared:
+        def __init__(self):
+            self.controller, self.active, self.calls, self.config = None, None, [], "cfg"
+
+        def set_adapter(self, name):
+            self.active = name
+
+        @property
+        def active_adapter(self):
+            return self.active
+
+        def forward(self, x, **kw):
+            self.calls.append((self.active, self.controller, x))
+            return x
+
+    sh = Shared()
+    rev, fwd = AdapterView(sh, "reverse"), AdapterView(sh, "forward")
+    assert rev.config == "cfg" and rev.supports_cond_only and rev.controller is None
+    rev.controller = "ctrl-r"
+    assert fwd.controller is None and sh.controller is None
+    assert rev(1) == 1 and fwd(2) == 2 and rev(3) == 3
+    assert sh.calls == [("reverse", "ctrl-r", 1), ("forward", None, 2), ("reverse", "ctrl-r", 3)]
+    assert sh.controller is None                      # restored after every call
+    assert graphs._cache_of(rev) is not graphs._cache_of(fwd)
+    rev.some_flag = 7                                 # anything else is state of the shared executor
+    assert sh.some_flag == 7
+
+
+def test_loading_adapter_mode_and_fp32_ops_surface(monkeypatch):
+    """`adapters=` validation / environment default, and the fp32 ops module offering every op the executor calls with
+    the signature of its fp16 counterpart (unet.B200UNet swaps the module, nothing else)."""
+    import inspect
+    from invertible_cd_b200 import loading, ops, ops_f32
+    assert loading._adapter_mode(None) == "resident" and loading._adapter_mode("swap") == "swap"
+    monkeypatch.setenv("ICD_LORA_ADAPTERS", "swap")
+    assert loading._adapter_mode(None) == "swap" and loading._adapter_mode("resident") == "resident"
+    with pytest.raises(ValueError):
+        loading._adapter_mode("both")
+    used = re.findall(r"\bops\.(\w+)\(", open(os.path.join(ROOT, "invertible_cd_b200", "unet.py")).read())
+    used = sorted(set(used) - {"attn_probs_from_stats"})      # fp16-only optimisation, bypassed when precision == fp32
+    assert {"linear", "conv3x3", "groupnorm", "layernorm", "attention", "attn_scores", "softmax_", "attn_pv"} <= set(used)
+    for name in used:
+        f16, f32 = inspect.signature(getattr(ops, name)), inspect.signature(getattr(ops_f32, name))
+        assert list(f16.parameters) == list(f32.parameters), (name, f16, f32)
